@@ -1,0 +1,125 @@
+/*
+ * rtb200.h -- C ABI of librtb200.so, the sm_100a CUDA implementation of the reference's
+ * render() hot path.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   rtb_scene_create*      the implicit "scene" = the Object[] the caller hands to
+ *                          render() (raytracer.h:156, main.c:256-397, main.c:429); here it
+ *                          is uploaded once, converted AoS-double -> SoA on the device and
+ *                          a BVH is built over it (replaces the O(n) loop of intersect(),
+ *                          raytracer.c:393-464)
+ *   rtb_render_accum       the loop nest of render() up to the per-pixel sum
+ *                          (raytracer.c:184-213): camera rays (raytracer.c:375-384),
+ *                          trace_path (raytracer.c:482-554), RNG (raytracer.c:227)
+ *   rtb_tonemap            mean, gamma 5.0, 8-bit truncation (raytracer.c:215-220)
+ *   rtb_render             the whole of render() (raytracer.c:176-223), host buffers in/out
+ *   rtb_trace_rays         intersect() for arbitrary rays (raytracer.c:393-464): parity probe
+ *   rtb_path_records       per-path vertex records: parity probe for the 1-bounce check
+ *   rtb_philox4x32_10      random_double()'s replacement (raytracer.c:227): KAT probe
+ *
+ * Array arguments named `objects` are arrays of the reference's own records:
+ *   - flat sphere record `Object`, 88 bytes (raytracer.h:104-111):
+ *       u32 flags @0, f64 radius @8, f64 center[3] @16, f64 color[3] @40, f64 emission[3] @64
+ *   - `SceneObject`, 96 bytes (the record commented out at raytracer.h:95-102):
+ *       i32 type @0 (0 sphere, 1 mesh), Material @8 {u32 flags @8, f64 color[3] @16,
+ *       f64 emission[3] @40, f64 ka,ks,kd @64}, pointer @88 to Sphere{f64 center[3], f64 radius}
+ *       or TriangleMesh{size_t num_triangles, Vertex* vertices}, Vertex = {f64 pos[3], f64 tex[2]}
+ * `camera` is the reference Camera (raytracer.h:121-124) viewed as 12 doubles:
+ *   position, horizontal, vertical, lower_left_corner.
+ *
+ * All functions return 0 on success or a negative RTB_E* code; rtb_last_error() gives the
+ * text (CUDA error string included).  There is no CPU fallback: without a usable CUDA
+ * device every compute entry point fails with RTB_ECUDA.
+ *
+ * Threading: a scene may be rendered from one host thread at a time.  Device pointers
+ * (`d_` prefix) belong to the scene's device; `stream` is a cudaStream_t (NULL = the
+ * legacy default stream).
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_OK 0
+#define RTB_EINVAL (-1)
+#define RTB_ECUDA (-2)
+#define RTB_ENOMEM (-3)
+
+#define RTB_DIELECTRIC_STOCHASTIC 0
+#define RTB_DIELECTRIC_SPLIT 1
+
+typedef struct rtb_scene rtb_scene; /* opaque: device-resident SoA geometry, materials, BVH */
+
+typedef struct
+{
+  int width, height;
+  int sample_begin, sample_end; /* global sample indices [begin, end) rendered by this call */
+  int max_depth;                /* run-time MAX_DEPTH (raytracer.h:25); path dies at depth > max_depth */
+  int dielectric_mode;          /* RTB_DIELECTRIC_* */
+  uint64_t seed;                /* Philox key */
+  int kernel;                   /* 0 = auto, 1 = megakernel, 2 = wavefront */
+  int reserved;
+} rtb_render_desc;
+
+typedef struct
+{
+  unsigned long long rays;            /* trace_path invocations (the reference's ray_count, raytracer.c:484) */
+  unsigned long long rays_intersected; /* of those, the ones that ran the scene query */
+  unsigned long long prim_tests;      /* exact primitive tests (intersection_test_count, raytracer.c:79,122) */
+  unsigned long long node_visits;     /* BVH nodes fetched */
+  unsigned long long paths;           /* camera samples */
+  unsigned long long launches;        /* kernels launched by the call */
+  float gpu_ms;                       /* CUDA-event time of the call's kernels on `stream` */
+  float build_ms;                     /* scene create only: upload + marshal + BVH build */
+} rtb_counters;
+
+typedef struct
+{
+  size_t n_objects, n_spheres, n_triangles;
+  size_t n_bvh_prims, n_bvh_nodes, n_big_prims;
+  size_t device_bytes;
+  float build_ms;
+  int bvh_depth;
+  int device;
+} rtb_scene_info;
+
+const char *rtb_last_error(void);
+const char *rtb_version(void);
+int rtb_device_count(void);
+
+/* scene: upload + marshal + BVH build (blocking) */
+int rtb_scene_create_objects(const void *objects88, size_t n_objects, int device, rtb_scene **out);
+int rtb_scene_create(const void *scene_objects96, size_t n_objects, int device, rtb_scene **out);
+int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info);
+void rtb_scene_destroy(rtb_scene *scene);
+
+/* d_accum: DEVICE float[height*width*3], OVERWRITTEN with the sum over the call's samples.
+ * Asynchronous on `stream` unless `counters` is non-NULL (then it synchronises to read them). */
+int rtb_render_accum(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
+                     float *d_accum, void *stream, rtb_counters *counters);
+
+/* d_fb: DEVICE u8[height*width*3] = trunc(255*clamp((accum/total_samples)^(1/5))) */
+int rtb_tonemap(const float *d_accum, int width, int height, int total_samples, uint8_t *d_fb,
+                int device, void *stream);
+
+/* whole render() with HOST buffers: framebuffer out, optional host float accum out */
+int rtb_render(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
+               uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters);
+
+/* parity probes (host buffers) */
+int rtb_trace_rays(rtb_scene *scene, const double *rays6, size_t n_rays, int use_bvh, int32_t *ids,
+                   int64_t *prims, double *ts, double *points, double *normals, double *uvs);
+int rtb_path_records(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc, int sample,
+                     int n_vertices, int32_t *ids, double *points, double *normals, double *dists,
+                     float *radiance);
+int rtb_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, size_t n, uint32_t *out4, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

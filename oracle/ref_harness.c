@@ -1,0 +1,268 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE.  Wraps the UNMODIFIED reference renderer so the
+ * tests can call its functions (including the `static` ones) directly.
+ *
+ * Nothing of the reference is copied: this translation unit textually includes
+ * /root/reference/raytracer.c where it lies (the Makefile passes -I$(REF)), and the
+ * result is written to oracle/_ref/libref.so, which is git-ignored.  It is only ever
+ * built in the container that has /root/reference; the GPU box uses the prebuilt .so.
+ *
+ * Three hooks are applied from the outside, without touching the reference text:
+ *   1. MAX_DEPTH (raytracer.h:25, no #ifndef guard) is re-defined AFTER the header was
+ *      included once, to a run-time variable.  The second #include of raytracer.h from
+ *      raytracer.c:7 is then a no-op thanks to its include guard.
+ *   2. `rand()` (the only RNG primitive, raytracer.c:227) is routed to ref_rand_hook(),
+ *      which either forwards to libc rand() (bit-for-bit the shipped behaviour) or
+ *      replays a caller-supplied stream of 31-bit integers, so the restatement in
+ *      oracle.c can be compared with the reference draw for draw.
+ *   3. `extern inline` declarations give vector.h's bare C99 inlines an external
+ *      definition.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product never does.
+ */
+#include "raytracer.h" /* the reference's, via -I/root/reference */
+
+static int g_ref_max_depth = 5;
+#undef MAX_DEPTH
+#define MAX_DEPTH (g_ref_max_depth)
+
+/* ---- rand() hook ----------------------------------------------------------- */
+
+static const int32_t *g_stream = NULL; /* NULL: libc rand() */
+static long long g_stream_len = 0;
+static long long g_stream_pos = 0;
+static long long g_stream_overrun = 0;
+
+static int ref_rand_hook(void)
+{
+  if (g_stream == NULL)
+    return (rand)();
+  if (g_stream_pos >= g_stream_len)
+  {
+    g_stream_overrun++;
+    return 0;
+  }
+  return (int)g_stream[g_stream_pos++];
+}
+#define rand() ref_rand_hook()
+
+#include "raytracer.c" /* the reference's renderer, unmodified */
+
+#undef rand
+
+/* external definitions for vector.h's inline functions */
+extern inline vec3 vec3_mult(vec3 a, vec3 b);
+extern inline vec3 vec3_sub(vec3 a, vec3 b);
+extern inline vec3 vec3_add(vec3 a, vec3 b);
+extern inline REAL vec3_dot(vec3 a, vec3 b);
+extern inline REAL vec3_length(vec3 v);
+extern inline vec3 vec3_scalar_mult(vec3 v, REAL s);
+extern inline vec3 vec3_scalar_div(vec3 v, REAL s);
+extern inline vec2 vec2_scalar_mult(vec2 v, REAL s);
+extern inline vec2 vec2_add(vec2 a, vec2 b);
+extern inline vec3 vec3_cross(vec3 a, vec3 b);
+extern inline int vec3_equal(vec3 a, vec3 b);
+extern inline vec3 vec3_normalize(vec3 v);
+extern inline vec3 mat4_vector_mult(mat4 A, vec3 v);
+extern inline void mat4_mult(mat4 A, mat4 B, mat4 C);
+
+/* ---- exported wrappers ------------------------------------------------------ */
+
+void ref_set_max_depth(int d) { g_ref_max_depth = d; }
+int ref_get_max_depth(void) { return g_ref_max_depth; }
+
+void ref_set_stream(const int32_t *stream, long long len)
+{
+  g_stream = stream;
+  g_stream_len = len;
+  g_stream_pos = 0;
+  g_stream_overrun = 0;
+}
+long long ref_stream_pos(void) { return g_stream_pos; }
+long long ref_stream_overrun(void) { return g_stream_overrun; }
+
+void ref_reset_counters(void)
+{
+  ray_count = 0;
+  intersection_test_count = 0;
+}
+long long ref_ray_count(void) { return ray_count; }
+long long ref_intersection_test_count(void) { return intersection_test_count; }
+
+size_t ref_sizeof(int which)
+{
+  switch (which)
+  {
+  case 0: return sizeof(Vertex);
+  case 1: return sizeof(Ray);
+  case 2: return sizeof(Material);
+  case 3: return sizeof(Sphere);
+  case 4: return sizeof(TriangleMesh);
+  case 5: return sizeof(Object);
+  case 6: return sizeof(Hit);
+  case 7: return sizeof(Camera);
+  case 8: return sizeof(Options);
+  default: return 0;
+  }
+}
+
+void ref_init_camera(Camera *camera, const double *pos, const double *target, int width, int height)
+{
+  Options o;
+  memset(&o, 0, sizeof(o));
+  o.width = width;
+  o.height = height;
+  init_camera(camera, (vec3){pos[0], pos[1], pos[2]}, (vec3){target[0], target[1], target[2]}, &o);
+}
+
+void ref_camera_ray(const Camera *camera, double u, double v, double *origin_dir6)
+{
+  Ray r = get_camera_ray(camera, u, v);
+  origin_dir6[0] = r.origin.x; origin_dir6[1] = r.origin.y; origin_dir6[2] = r.origin.z;
+  origin_dir6[3] = r.direction.x; origin_dir6[4] = r.direction.y; origin_dir6[5] = r.direction.z;
+}
+
+/* the shipped render(): single OpenMP thread + srand(seed) is bit-deterministic */
+void ref_render(uint8_t *fb, Object *objects, size_t n, Camera *camera, int width, int height,
+                int samples, unsigned seed, int max_depth, int threads)
+{
+  Options o;
+  memset(&o, 0, sizeof(o));
+  o.width = width;
+  o.height = height;
+  o.samples = samples;
+  g_ref_max_depth = max_depth;
+  g_stream = NULL;
+  omp_set_num_threads(threads > 0 ? threads : 1);
+  srand(seed);
+  /* the reference prints a progress bar from inside render(); keep stdout clean */
+  FILE *saved = stdout;
+  FILE *sink = fopen("/dev/null", "w");
+  if (sink) stdout = sink;
+  render(fb, objects, n, camera, &o);
+  if (sink) { stdout = saved; fclose(sink); }
+}
+
+/* Same loop nest as render() (raytracer.c:184-223) but returning the double mean per
+ * pixel before gamma, so float accumulation on the GPU can be compared without the 8-bit
+ * truncation.  Uses the reference's own get_camera_ray / trace_path and libc rand(). */
+void ref_render_mean(double *mean_rgb, Object *objects, size_t n, Camera *camera, int width,
+                     int height, int samples, unsigned seed, int max_depth)
+{
+  g_ref_max_depth = max_depth;
+  g_stream = NULL;
+  srand(seed);
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++)
+    {
+      vec3 pixel = {0, 0, 0};
+      for (int s = 0; s < samples; s++)
+      {
+        double u = (double)(x + random_double()) / ((double)width - 1.0);
+        double v = (double)(y + random_double()) / ((double)height - 1.0);
+        Ray ray = get_camera_ray(camera, u, v);
+        vec3 sample = trace_path(&ray, objects, n, 0);
+        pixel = vec3_add(pixel, sample);
+      }
+      pixel = vec3_scalar_mult(pixel, 1.0 / (double)samples);
+      double *o = mean_rgb + 3 * ((size_t)y * width + x);
+      o[0] = pixel.x; o[1] = pixel.y; o[2] = pixel.z;
+    }
+}
+
+/* Nearest hit of arbitrary rays through the reference's static intersect().
+ * rays: n x 6 doubles (origin, direction).  Outputs per ray: id (-1 on a miss),
+ * point[3], normal[3], uv[2], last_t (the quirky Hit.t, quirk Q9). */
+void ref_intersect_rays(Object *objects, size_t n_obj, const double *rays, long long n_rays,
+                        int32_t *ids, double *points, double *normals, double *uvs, double *last_t)
+{
+  for (long long i = 0; i < n_rays; i++)
+  {
+    const double *r = rays + 6 * i;
+    Ray ray = {{r[0], r[1], r[2]}, {r[3], r[4], r[5]}};
+    Hit hit = {.t = DBL_MAX};
+    bool ok = intersect(&ray, objects, n_obj, &hit);
+    ids[i] = ok ? (int32_t)hit.object_id : -1;
+    if (points)  { points[3 * i] = ok ? hit.point.x : 0; points[3 * i + 1] = ok ? hit.point.y : 0; points[3 * i + 2] = ok ? hit.point.z : 0; }
+    if (normals) { normals[3 * i] = ok ? hit.normal.x : 0; normals[3 * i + 1] = ok ? hit.normal.y : 0; normals[3 * i + 2] = ok ? hit.normal.z : 0; }
+    if (uvs)     { uvs[2 * i] = ok ? hit.u : 0; uvs[2 * i + 1] = ok ? hit.v : 0; }
+    if (last_t)  last_t[i] = hit.t;
+  }
+}
+
+/* One path through the reference's static trace_path(), its rand() calls replayed from
+ * `stream`.  Returns the number of draws consumed. */
+long long ref_trace_path_stream(Object *objects, size_t n_obj, const double *ray6, int depth,
+                                int max_depth, const int32_t *stream, long long stream_len,
+                                double *radiance3)
+{
+  g_ref_max_depth = max_depth;
+  ref_set_stream(stream, stream_len);
+  Ray ray = {{ray6[0], ray6[1], ray6[2]}, {ray6[3], ray6[4], ray6[5]}};
+  vec3 c = trace_path(&ray, objects, n_obj, depth);
+  radiance3[0] = c.x; radiance3[1] = c.y; radiance3[2] = c.z;
+  long long used = g_stream_overrun ? -1 : g_stream_pos;
+  g_stream = NULL;
+  return used;
+}
+
+/* leaf primitives and helpers, for known-answer comparisons */
+int ref_intersect_sphere(const double *ray6, const double *center, double radius, double *t)
+{
+  Ray ray = {{ray6[0], ray6[1], ray6[2]}, {ray6[3], ray6[4], ray6[5]}};
+  Hit h = {.t = DBL_MAX};
+  bool ok = intersect_sphere(&ray, (vec3){center[0], center[1], center[2]}, radius, &h);
+  *t = h.t;
+  return ok;
+}
+
+/* verts: 3 x (pos[3], tex[2]) = 15 doubles; out: t, u, v */
+int ref_intersect_triangle(const double *ray6, const double *verts, double *tuv)
+{
+  Ray ray = {{ray6[0], ray6[1], ray6[2]}, {ray6[3], ray6[4], ray6[5]}};
+  Vertex v[3];
+  for (int k = 0; k < 3; k++)
+  {
+    v[k].pos = (vec3){verts[5 * k], verts[5 * k + 1], verts[5 * k + 2]};
+    v[k].tex = (vec2){verts[5 * k + 3], verts[5 * k + 4]};
+  }
+  Hit h = {.t = DBL_MAX, .u = 0, .v = 0};
+  bool ok = intersect_triangle(&ray, v[0], v[1], v[2], &h);
+  tuv[0] = h.t; tuv[1] = h.u; tuv[2] = h.v;
+  return ok;
+}
+
+void ref_surface_normal(const double *v9, double *n3)
+{
+  vec3 n = calculate_surface_normal((vec3){v9[0], v9[1], v9[2]}, (vec3){v9[3], v9[4], v9[5]},
+                                    (vec3){v9[6], v9[7], v9[8]});
+  n3[0] = n.x; n3[1] = n.y; n3[2] = n.z;
+}
+
+void ref_reflect(const double *in3, const double *n3, double *out3)
+{
+  vec3 r = reflect((vec3){in3[0], in3[1], in3[2]}, (vec3){n3[0], n3[1], n3[2]});
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
+void ref_refract(const double *in3, const double *n3, double iot, double *out3)
+{
+  vec3 r = refract((vec3){in3[0], in3[1], in3[2]}, (vec3){n3[0], n3[1], n3[2]}, iot);
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
+void ref_checkered(const double *color3, double u, double v, double M, double *out3)
+{
+  vec3 r = checkered_texture((vec3){color3[0], color3[1], color3[2]}, u, v, M);
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
+double ref_random_double_from(int32_t r31)
+{
+  int32_t s[1] = {r31};
+  ref_set_stream(s, 1);
+  double d = random_double();
+  g_stream = NULL;
+  return d;
+}

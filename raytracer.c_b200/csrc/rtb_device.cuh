@@ -1,0 +1,433 @@
+/*
+ * rtb_device.cuh -- device-side building blocks of the path tracer (sm_100a).
+ *
+ * Numerics contract (DESIGN.md "Precision"):
+ *   - everything that decides WHICH primitive is hit, and where, is IEEE double with the
+ *     reference's operation order and NO fused multiply-add (the reference is built with
+ *     ISO-C gcc on x86-64: no contraction).  The __d*_rn intrinsics are never contracted
+ *     by nvcc, so t, the hit point and the normal are bit-identical to the reference's
+ *     for the same ray;
+ *   - the BVH is walked in FP32 with conservatively padded boxes: it only PROPOSES
+ *     candidates, the double test disposes;
+ *   - colour arithmetic (throughput, emission) is FP32.
+ */
+#ifndef RTB_DEVICE_CUH
+#define RTB_DEVICE_CUH
+
+#include "rtb_internal.h"
+#include <float.h>
+
+/* ---- double3 without contraction (vector.h:16-61 operation order) ---------- */
+
+struct d3 { double x, y, z; };
+
+__device__ __forceinline__ d3 d3_make(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ d3 d3_add(d3 a, d3 b) { return d3_make(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y), __dadd_rn(a.z, b.z)); }
+__device__ __forceinline__ d3 d3_sub(d3 a, d3 b) { return d3_make(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)); }
+__device__ __forceinline__ d3 d3_scale(d3 v, double s) { return d3_make(__dmul_rn(v.x, s), __dmul_rn(v.y, s), __dmul_rn(v.z, s)); }
+__device__ __forceinline__ double d3_dot(d3 a, d3 b)
+{
+  return __dadd_rn(__dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ d3 d3_cross(d3 a, d3 b)
+{
+  return d3_make(__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)),
+                 __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
+                 __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ double d3_length(d3 v) { return __dsqrt_rn(d3_dot(v, v)); }
+/* vec3_normalize: multiply by the reciprocal of the length (vector.h:56-61) */
+__device__ __forceinline__ d3 d3_normalize(d3 v) { return d3_scale(v, __ddiv_rn(1.0, d3_length(v))); }
+__device__ __forceinline__ d3 d3_neg(d3 v) { return d3_make(-v.x, -v.y, -v.z); }
+
+/* ---- Philox4x32-10 (replaces random_double, raytracer.c:227) --------------- */
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+  for (int round = 0; round < 10; round++)
+  {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+/* 32-bit word -> the reference's 31-bit uniform in [0,1): (w>>1) / 2^31, exact */
+__device__ __forceinline__ double uniform31(unsigned w) { return (double)(w >> 1) * (1.0 / 2147483648.0); }
+
+/* ---- exact primitive tests -------------------------------------------------- */
+
+#define RT_EPSILON 1e-8 /* raytracer.h:24 */
+
+/* raytracer.c:77-118, operation for operation */
+__device__ __forceinline__ bool sphere_exact(const d3 &o, const d3 &d, double cx, double cy, double cz,
+                                             double radius, double &t_out)
+{
+  d3 L = d3_make(__dsub_rn(cx, o.x), __dsub_rn(cy, o.y), __dsub_rn(cz, o.z));
+  double tca = d3_dot(L, d);
+  if (tca < 0)
+    return false;
+  double d2 = __dsub_rn(d3_dot(L, L), __dmul_rn(tca, tca));
+  double r2 = __dmul_rn(radius, radius);
+  if (d2 > r2)
+    return false;
+  double thc = __dsqrt_rn(__dsub_rn(r2, d2));
+  double t0 = __dsub_rn(tca, thc);
+  double t1 = __dadd_rn(tca, thc);
+  if (t0 > t1)
+  {
+    double s = t0;
+    t0 = t1;
+    t1 = s;
+  }
+  if (t0 < 0)
+  {
+    t0 = t1;
+    if (t0 < 0)
+      return false;
+  }
+  if (t0 > RT_EPSILON)
+  {
+    t_out = t0;
+    return true;
+  }
+  return false;
+}
+
+/* raytracer.c:120-174 (Moeller-Trumbore), operation for operation; bu,bv = barycentrics */
+__device__ __forceinline__ bool triangle_exact(const d3 &o, const d3 &d, const d3 &v0, const d3 &v1,
+                                               const d3 &v2, double &t_out, double &bu, double &bv)
+{
+  d3 e1 = d3_sub(v1, v0);
+  d3 e2 = d3_sub(v2, v0);
+  d3 h = d3_cross(d, e2);
+  double det = d3_dot(e1, h);
+  if (det > -RT_EPSILON && det < RT_EPSILON)
+    return false;
+  double f = __ddiv_rn(1.0, det);
+  d3 s = d3_sub(o, v0);
+  double u = __dmul_rn(f, d3_dot(s, h));
+  if (u < 0.0 || u > 1.0)
+    return false;
+  d3 q = d3_cross(s, e1);
+  double v = __dmul_rn(f, d3_dot(d, q));
+  if (v < 0.0 || __dadd_rn(u, v) > 1.0)
+    return false;
+  double t = __dmul_rn(f, d3_dot(e2, q));
+  if (t > RT_EPSILON)
+  {
+    t_out = t;
+    bu = u;
+    bv = v;
+    return true;
+  }
+  return false;
+}
+
+/* ---- primitive records ------------------------------------------------------ */
+
+__device__ __forceinline__ double rec_double(float lo, float hi)
+{
+  return __hiloint2double(__float_as_int(hi), __float_as_int(lo));
+}
+
+struct PrimView
+{
+  float4 a, b, c;
+  __device__ __forceinline__ bool is_sphere() const { return (__float_as_uint(c.z) & RTB_PRIM_SPHERE_BIT) != 0; }
+  __device__ __forceinline__ int gid() const { return __float_as_int(c.y); }
+  __device__ __forceinline__ int object() const { return (int)(__float_as_uint(c.z) & 0x7FFFFFFFu); }
+  __device__ __forceinline__ double cx() const { return rec_double(a.x, a.y); }
+  __device__ __forceinline__ double cy() const { return rec_double(a.z, a.w); }
+  __device__ __forceinline__ double cz() const { return rec_double(b.x, b.y); }
+  __device__ __forceinline__ double radius() const { return rec_double(b.z, b.w); }
+  __device__ __forceinline__ d3 v0() const { return d3_make((double)a.x, (double)a.y, (double)a.z); }
+  __device__ __forceinline__ d3 v1() const { return d3_make((double)a.w, (double)b.x, (double)b.y); }
+  __device__ __forceinline__ d3 v2() const { return d3_make((double)b.z, (double)b.w, (double)c.x); }
+};
+
+__device__ __forceinline__ PrimView load_prim(const float4 *__restrict__ base, int index)
+{
+  PrimView p;
+  p.a = __ldg(base + 3 * index + 0);
+  p.b = __ldg(base + 3 * index + 1);
+  p.c = __ldg(base + 3 * index + 2);
+  return p;
+}
+
+/* nearest-hit bookkeeping: strict `<` in index order == lowest gid wins equal t
+ * (raytracer.c:404) */
+struct HitRec
+{
+  double t;
+  int gid;
+  int slot; /* >= 0: index into the BVH-ordered array; < 0: ~index into the big list */
+};
+
+__device__ __forceinline__ void test_prim(const PrimView &p, int slot, const d3 &o, const d3 &d, HitRec &best)
+{
+  double t, bu, bv;
+  bool hit;
+  if (p.is_sphere())
+    hit = sphere_exact(o, d, p.cx(), p.cy(), p.cz(), p.radius(), t);
+  else
+    hit = triangle_exact(o, d, p.v0(), p.v1(), p.v2(), t, bu, bv);
+  if (hit)
+  {
+    int gid = p.gid();
+    if (t < best.t || (t == best.t && gid < best.gid))
+    {
+      best.t = t;
+      best.gid = gid;
+      best.slot = slot;
+    }
+  }
+}
+
+/* ---- nearest hit: big list + FP32 BVH walk with exact leaf tests ------------ */
+
+struct TraceStats
+{
+  unsigned prim_tests, node_visits;
+};
+
+template <bool STATS>
+__device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best,
+                                            TraceStats &st)
+{
+  best.t = DBL_MAX;
+  best.gid = 0x7FFFFFFF;
+  best.slot = 0;
+  bool found_any = false;
+  (void)found_any;
+
+  /* oversized primitives (the r=10000 wall spheres): tested for every ray, exactly */
+  for (int k = 0; k < sv.n_big; k++)
+  {
+    PrimView p = load_prim(sv.big, k);
+    test_prim(p, ~k, o, d, best);
+    if (STATS) st.prim_tests++;
+  }
+  if (sv.n_prims == 0)
+    return;
+
+  /* FP32 ray for the walk.  If the origin lies outside the guard box the ray is first
+   * advanced (in double) to just before its entry point so that float rounding of the
+   * origin stays within the padding the boxes were built with. */
+  float ofx = (float)o.x, ofy = (float)o.y, ofz = (float)o.z;
+  float dfx = (float)d.x, dfy = (float)d.y, dfz = (float)d.z;
+  const float tiny = 1e-24f;
+  if (fabsf(dfx) < tiny) dfx = copysignf(tiny, dfx);
+  if (fabsf(dfy) < tiny) dfy = copysignf(tiny, dfy);
+  if (fabsf(dfz) < tiny) dfz = copysignf(tiny, dfz);
+  float idx = 1.0f / dfx, idy = 1.0f / dfy, idz = 1.0f / dfz;
+  double t_base = 0.0;
+  {
+    bool outside = ofx < sv.guard_lo[0] || ofx > sv.guard_hi[0] || ofy < sv.guard_lo[1] ||
+                   ofy > sv.guard_hi[1] || ofz < sv.guard_lo[2] || ofz > sv.guard_hi[2];
+    if (outside)
+    {
+      float ax = (sv.guard_lo[0] - ofx) * idx, bx = (sv.guard_hi[0] - ofx) * idx;
+      float ay = (sv.guard_lo[1] - ofy) * idy, by = (sv.guard_hi[1] - ofy) * idy;
+      float az = (sv.guard_lo[2] - ofz) * idz, bz = (sv.guard_hi[2] - ofz) * idz;
+      float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+      float t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+      /* the guard box is far larger than the padded scene box, so this rough FP32 test
+       * cannot reject a ray that touches the scene box */
+      if (t_out < 0.0f || t_in > t_out * 1.001f + 1e-3f)
+        return;
+      if (t_in > 0.0f)
+      {
+        t_base = (double)(t_in * 0.999f);
+        ofx = (float)fma(d.x, t_base, o.x);
+        ofy = (float)fma(d.y, t_base, o.y);
+        ofz = (float)fma(d.z, t_base, o.z);
+      }
+    }
+  }
+  const float oodx = ofx * idx, oody = ofy * idy, oodz = ofz * idz;
+  const float widen = 1.0000005f; /* > (1+2^-23)^4: slab arithmetic rounding */
+
+  /* upper bound of the parametric distance still worth visiting, in the re-based FP32 frame */
+  float tmax = (best.t >= 1e30) ? 3.0e38f : __double2float_ru((best.t - t_base)) * widen;
+
+  int stack_ref[RTB_STACK_SIZE];
+  float stack_t[RTB_STACK_SIZE];
+  int sp = 0;
+  int cur = sv.root_ref;
+
+  while (true)
+  {
+    if (cur >= 0)
+    {
+      if (STATS) st.node_visits++;
+      const float4 n0 = __ldg(sv.nodes + 4 * cur + 0);
+      const float4 n1 = __ldg(sv.nodes + 4 * cur + 1);
+      const float4 n2 = __ldg(sv.nodes + 4 * cur + 2);
+      const float4 n3 = __ldg(sv.nodes + 4 * cur + 3);
+
+      float c0lx = fmaf(n0.x, idx, -oodx), c0hx = fmaf(n0.y, idx, -oodx);
+      float c0ly = fmaf(n0.z, idy, -oody), c0hy = fmaf(n0.w, idy, -oody);
+      float c0lz = fmaf(n2.x, idz, -oodz), c0hz = fmaf(n2.y, idz, -oodz);
+      float c1lx = fmaf(n1.x, idx, -oodx), c1hx = fmaf(n1.y, idx, -oodx);
+      float c1ly = fmaf(n1.z, idy, -oody), c1hy = fmaf(n1.w, idy, -oody);
+      float c1lz = fmaf(n2.z, idz, -oodz), c1hz = fmaf(n2.w, idz, -oodz);
+
+      float c0min = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.0f));
+      float c0max = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fminf(fmaxf(c0lz, c0hz), tmax));
+      float c1min = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.0f));
+      float c1max = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fminf(fmaxf(c1lz, c1hz), tmax));
+
+      bool h0 = c0min <= c0max * widen;
+      bool h1 = c1min <= c1max * widen;
+      int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+
+      if (h0 && h1)
+      {
+        bool swap = c1min < c0min;
+        int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
+        float far_t = swap ? c0min : c1min;
+        stack_ref[sp] = far_ref;
+        stack_t[sp] = far_t;
+        sp++;
+        cur = near_ref;
+        continue;
+      }
+      if (h0) { cur = r0; continue; }
+      if (h1) { cur = r1; continue; }
+    }
+    else
+    {
+      /* leaf: exact double tests */
+      int code = ~cur;
+      int first = code >> 3, count = (code & 7) + 1;
+      for (int k = 0; k < count; k++)
+      {
+        PrimView p = load_prim(sv.prims, first + k);
+        test_prim(p, first + k, o, d, best);
+      }
+      if (STATS) st.prim_tests += count;
+      if (best.t < 1e30)
+        tmax = __double2float_ru(best.t - t_base) * widen;
+    }
+    /* pop, skipping subtrees that start beyond the current best */
+    bool got = false;
+    while (sp > 0)
+    {
+      sp--;
+      if (stack_t[sp] <= tmax)
+      {
+        cur = stack_ref[sp];
+        got = true;
+        break;
+      }
+    }
+    if (!got)
+      break;
+  }
+}
+
+/* brute force over every primitive: the reference's own O(n) loop (raytracer.c:401-456),
+ * kept as a debug path for the BVH == brute-force parity test */
+__device__ __forceinline__ void closest_hit_bruteforce(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best)
+{
+  best.t = DBL_MAX;
+  best.gid = 0x7FFFFFFF;
+  best.slot = 0;
+  for (int k = 0; k < sv.n_big; k++)
+    test_prim(load_prim(sv.big, k), ~k, o, d, best);
+  for (int k = 0; k < sv.n_prims; k++)
+    test_prim(load_prim(sv.prims, k), k, o, d, best);
+}
+
+/* ---- surface at the nearest hit (raytracer.c:406-411, :428-431) ------------- */
+
+struct Surface
+{
+  d3 point, normal;
+  int object;
+  double u, v; /* only filled when want_uv */
+};
+
+__device__ __forceinline__ Surface surface_at(const SceneView &sv, const d3 &o, const d3 &d, const HitRec &best,
+                                              bool want_uv)
+{
+  Surface s;
+  PrimView p = best.slot >= 0 ? load_prim(sv.prims, best.slot) : load_prim(sv.big, ~best.slot);
+  s.object = p.object();
+  s.point = d3_add(o, d3_scale(d, best.t)); /* point_at, raytracer.c:257 */
+  s.u = 0.0;
+  s.v = 0.0;
+  if (p.is_sphere())
+  {
+    d3 c = d3_make(p.cx(), p.cy(), p.cz());
+    s.normal = d3_normalize(d3_sub(s.point, c));
+    if (want_uv)
+    {
+      const double RT_PI = 3.14159265359; /* raytracer.h:22 */
+      s.u = __dadd_rn(__ddiv_rn(atan2(s.normal.x, s.normal.z), __dmul_rn(2.0, RT_PI)), 0.5);
+      s.v = __dadd_rn(__dmul_rn(s.normal.y, 0.5), 0.5);
+    }
+  }
+  else
+  {
+    d3 v0 = p.v0(), v1 = p.v1(), v2 = p.v2();
+    s.normal = d3_normalize(d3_cross(d3_sub(v2, v0), d3_sub(v1, v0))); /* raytracer.c:44 */
+    if (want_uv && sv.tex != nullptr && best.slot >= 0)
+    {
+      double t, bu, bv;
+      if (triangle_exact(o, d, v0, v1, v2, t, bu, bv))
+      {
+        float2 t0 = __ldg(sv.tex + 3 * best.slot + 0);
+        float2 t1 = __ldg(sv.tex + 3 * best.slot + 1);
+        float2 t2 = __ldg(sv.tex + 3 * best.slot + 2);
+        double w0 = __dsub_rn(__dsub_rn(1.0, bu), bv); /* 1 - u - v, raytracer.c:160 */
+        s.u = __dadd_rn(__dadd_rn(__dmul_rn((double)t0.x, w0), __dmul_rn((double)t1.x, bu)), __dmul_rn((double)t2.x, bv));
+        s.v = __dadd_rn(__dadd_rn(__dmul_rn((double)t0.y, w0), __dmul_rn((double)t1.y, bu)), __dmul_rn((double)t2.y, bv));
+      }
+    }
+  }
+  return s;
+}
+
+/* ---- camera (raytracer.c:375-384) ------------------------------------------- */
+
+struct CameraView
+{
+  double pos[3], horizontal[3], vertical[3], llc[3];
+};
+
+__device__ __forceinline__ void camera_ray(const CameraView &c, double u, double v, d3 &o, d3 &d)
+{
+  d3 pos = d3_make(c.pos[0], c.pos[1], c.pos[2]);
+  d3 H = d3_make(c.horizontal[0], c.horizontal[1], c.horizontal[2]);
+  d3 V = d3_make(c.vertical[0], c.vertical[1], c.vertical[2]);
+  d3 llc = d3_make(c.llc[0], c.llc[1], c.llc[2]);
+  d3 on_plane = d3_add(llc, d3_add(d3_scale(H, u), d3_scale(V, v)));
+  o = pos;
+  d = d3_normalize(d3_sub(pos, on_plane));
+}
+
+/* ---- scatter helpers ---------------------------------------------------------- */
+
+/* raytracer.c:349-352 */
+__device__ __forceinline__ d3 reflect_dir(const d3 &in, const d3 &n)
+{
+  return d3_sub(in, d3_scale(n, __dmul_rn(2.0, d3_dot(in, n))));
+}
+
+/* raytracer.c:386-391: factor 0.3 or 0.7 */
+__device__ __forceinline__ float checker_factor(double u, double v, double M)
+{
+  bool a = fmod(__dmul_rn(u, M), 1.0) > 0.5;
+  bool b = fmod(__dmul_rn(v, M), 1.0) < 0.5;
+  double on = (a ^ b) ? 1.0 : 0.0;
+  return (float)__dadd_rn(__dmul_rn(0.3, __dsub_rn(1.0, on)), __dmul_rn(0.7, on));
+}
+
+#endif /* RTB_DEVICE_CUH */

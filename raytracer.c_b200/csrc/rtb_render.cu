@@ -1,0 +1,665 @@
+/*
+ * rtb_render.cu -- the path-tracing kernels and the render / probe entry points.
+ *
+ * k_render is a "megakernel with path regeneration": one thread owns one pixel and a
+ * contiguous range of that pixel's samples.  Every loop iteration is one trace_path
+ * invocation of the reference (raytracer.c:482-554): nearest hit, Russian roulette,
+ * scatter.  When a path ends the lane starts the pixel's next sample in the same
+ * iteration slot, so lanes stay busy until their whole sample range is done; the warp
+ * re-converges once per iteration at the __all_sync at the top of the loop.
+ * Warps map to 8x4 pixel tiles so primary rays are coherent.
+ *
+ * Random numbers: Philox4x32-10, counter = (pixel, sample, bounce | 0x100, block),
+ * key = seed (see rtb_device.cuh and oracle/oracle.c for the layout; both sides must
+ * agree word for word).
+ */
+#include "rtb_device.cuh"
+
+#include <algorithm>
+#include <vector>
+#include <cstring>
+
+struct RenderArgs
+{
+  SceneView sv;
+  CameraView cam;
+  int width, height, tiles_x, n_tiles;
+  int s_begin, s_end, chunk, splits;
+  int max_depth, dielectric_mode;
+  uint2 key;
+  float *out; /* [splits][height*width*3] */
+  unsigned long long *counters;
+};
+
+struct PathState
+{
+  d3 o, d;
+  float tr, tg, tb; /* throughput */
+  int depth;
+  bool alive;
+};
+
+struct PathCounters
+{
+  unsigned rays, rays_hit;
+};
+
+#define RT_BACKGROUND (10.0f / 255.0f) /* raytracer.h:46, also returned on a depth cut (quirk Q2) */
+
+__device__ __forceinline__ void path_begin(const RenderArgs &A, PathState &st, int x, int y, unsigned pixel, unsigned sample)
+{
+  /* jitter: u = (x + xi1)/(W-1), v = (y + xi2)/(H-1), raytracer.c:203-204 */
+  uint4 w = philox4x32_10(make_uint4(pixel, sample, 0xFFFFFFFFu, 0u), A.key);
+  double u = __ddiv_rn(__dadd_rn((double)x, uniform31(w.x)), __dsub_rn((double)A.width, 1.0));
+  double v = __ddiv_rn(__dadd_rn((double)y, uniform31(w.y)), __dsub_rn((double)A.height, 1.0));
+  camera_ray(A.cam, u, v, st.o, st.d);
+  st.tr = st.tg = st.tb = 1.0f;
+  st.depth = 0;
+  st.alive = true;
+}
+
+/* One vertex of the path: the body of trace_path after the scene query.
+ * `sum` accumulates throughput * (emission | background). */
+__device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, const HitRec &best, unsigned pixel,
+                                           unsigned sample, float &sr, float &sg, float &sb, PathCounters &pc,
+                                           Surface *surf_out)
+{
+  if (best.t >= 1e300)
+  {
+    sr += st.tr * RT_BACKGROUND; sg += st.tg * RT_BACKGROUND; sb += st.tb * RT_BACKGROUND;
+    st.alive = false;
+    return;
+  }
+  /* material first: uv is only needed for checkered objects */
+  int slot_obj;
+  {
+    const float4 *rec = best.slot >= 0 ? A.sv.prims + 3 * best.slot : A.sv.big + 3 * (~best.slot);
+    slot_obj = (int)(__float_as_uint(__ldg(rec + 2).z) & 0x7FFFFFFFu);
+  }
+  const float4 m0 = __ldg(A.sv.mats + 2 * slot_obj + 0);
+  const float4 m1 = __ldg(A.sv.mats + 2 * slot_obj + 1);
+  const unsigned flags = __float_as_uint(m1.w);
+  Surface s = surface_at(A.sv, st.o, st.d, best, (flags & RT_M_CHECKERED) != 0);
+  if (surf_out)
+    *surf_out = s;
+
+  /* emission is added whether or not the path survives (raytracer.c:502,553) */
+  sr += st.tr * m1.x; sg += st.tg * m1.y; sb += st.tb * m1.z;
+
+  /* Russian roulette, one draw per vertex (raytracer.c:497-502) */
+  const unsigned bounce_word = (unsigned)st.depth | 0x100u;
+  uint4 w = philox4x32_10(make_uint4(pixel, sample, bounce_word, 0u), A.key);
+  if ((w.x >> 1) >= __float_as_uint(m0.w))
+  {
+    st.alive = false;
+    return;
+  }
+  st.tr *= m0.x; st.tg *= m0.y; st.tb *= m0.z; /* albedo / prob */
+  if (flags & RT_M_CHECKERED)
+  {
+    float c = checker_factor(s.u, s.v, 100000.0); /* raytracer.c:508 */
+    st.tr *= c; st.tg *= c; st.tb *= c;
+  }
+
+  if (flags & RT_M_REFRACTION)
+  {
+    /* raytracer.c:514-529.  refract(-d, n, 1.0) returns -d (quirk Q3), so the "refracted"
+     * ray is the retro-ray normalize(-d); the reflected one is normalize(reflect(d, n)).
+     * The reference traces both; here one is chosen with p = clamp(kr, .05, .95) and
+     * weighted kr/p or kt/(1-p) -- the same expectation. */
+    double facing = -d3_dot(st.d, s.normal);
+    double fresnel = __dadd_rn(__dmul_rn(1.0, 0.1), __dmul_rn(pow(__dsub_rn(1.0, facing), 3.0), __dsub_rn(1.0, 0.1)));
+    double kr = fresnel;
+    double kt = __dmul_rn(__dsub_rn(1.0, fresnel), 1.0);
+    double p = kr < 0.05 ? 0.05 : (kr > 0.95 ? 0.95 : kr);
+    float wgt;
+    if (uniform31(w.y) < p)
+    {
+      st.d = d3_normalize(reflect_dir(d3_scale(st.d, 1.0), s.normal));
+      wgt = (float)__ddiv_rn(kr, p);
+    }
+    else
+    {
+      st.d = d3_normalize(d3_scale(st.d, -1.0));
+      wgt = (float)__ddiv_rn(kt, __dsub_rn(1.0, p));
+    }
+    st.tr *= wgt; st.tg *= wgt; st.tb *= wgt;
+  }
+  else if (flags & RT_M_REFLECTION)
+  {
+    st.d = reflect_dir(st.d, s.normal); /* not renormalised (quirk Q8) */
+  }
+  else
+  {
+    /* uniform direction by cube rejection, flipped into the normal's hemisphere; weight
+     * cos(theta), no pdf (raytracer.c:231-253,545-551; quirk Q5) */
+    d3 p;
+    unsigned k = 0;
+    uint4 r = w;
+    double px = uniform31(r.y), py = uniform31(r.z), pz = uniform31(r.w);
+    while (true)
+    {
+      p = d3_make(__dadd_rn(__dmul_rn(px, 2.0), -1.0), __dadd_rn(__dmul_rn(py, 2.0), -1.0),
+                  __dadd_rn(__dmul_rn(pz, 2.0), -1.0));
+      if (!(d3_length(p) > 1.0) || k >= 98u)
+        break;
+      k++;
+      r = philox4x32_10(make_uint4(pixel, sample, bounce_word, k), A.key);
+      px = uniform31(r.x); py = uniform31(r.y); pz = uniform31(r.z);
+    }
+    d3 dir = d3_normalize(p);
+    if (d3_dot(dir, s.normal) < 0)
+      dir = d3_scale(dir, -1.0);
+    float c = (float)d3_dot(dir, s.normal);
+    st.d = dir;
+    st.tr *= c; st.tg *= c; st.tb *= c;
+  }
+  st.o = s.point;
+  st.depth++;
+  if (st.depth > A.max_depth)
+  {
+    /* the next trace_path call returns BACKGROUND without intersecting (raytracer.c:487) */
+    pc.rays++;
+    sr += st.tr * RT_BACKGROUND; sg += st.tg * RT_BACKGROUND; sb += st.tb * RT_BACKGROUND;
+    st.alive = false;
+  }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_render(const __grid_constant__ RenderArgs A)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int tile = warp % A.n_tiles;
+  const int split = warp / A.n_tiles;
+  const int x = (tile % A.tiles_x) * 8 + (lane & 7);
+  const int y = (tile / A.tiles_x) * 4 + (lane >> 3);
+  const bool valid = x < A.width && y < A.height && split < A.splits;
+  const unsigned pixel = (unsigned)(y * A.width + x);
+
+  int s = A.s_begin + split * A.chunk;
+  const int s_end = valid ? min(A.s_end, s + A.chunk) : s;
+
+  PathState st;
+  st.alive = false;
+  st.depth = 0;
+  st.tr = st.tg = st.tb = 0.0f;
+  st.o = d3_make(0, 0, 0);
+  st.d = d3_make(0, 0, 1);
+  float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+  PathCounters pc = { 0u, 0u };
+  TraceStats ts = { 0u, 0u };
+  unsigned paths = 0;
+
+  while (true)
+  {
+    if (!st.alive && s < s_end)
+    {
+      path_begin(A, st, x, y, pixel, (unsigned)s);
+      paths++;
+    }
+    if (__all_sync(0xFFFFFFFFu, !st.alive))
+      break;
+    if (st.alive)
+    {
+      HitRec best;
+      pc.rays++;
+      pc.rays_hit++;
+      closest_hit<STATS>(A.sv, st.o, st.d, best, ts);
+      path_shade(A, st, best, pixel, (unsigned)s, sr, sg, sb, pc, nullptr);
+      if (!st.alive)
+        s++;
+    }
+  }
+
+  if (valid)
+  {
+    float *o = A.out + ((size_t)split * A.width * A.height + pixel) * 3;
+    o[0] = sr; o[1] = sg; o[2] = sb;
+  }
+
+  /* counters: warp reduce, one atomic per warp and counter */
+  unsigned long long c0 = pc.rays, c1 = pc.rays_hit, c2 = ts.prim_tests, c3 = ts.node_visits, c4 = paths;
+  for (int off = 16; off > 0; off >>= 1)
+  {
+    c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, off);
+    c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, off);
+    c4 += __shfl_xor_sync(0xFFFFFFFFu, c4, off);
+    if (STATS)
+    {
+      c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, off);
+      c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, off);
+    }
+  }
+  if (lane == 0)
+  {
+    atomicAdd(&A.counters[0], c0);
+    atomicAdd(&A.counters[1], c1);
+    atomicAdd(&A.counters[4], c4);
+    if (STATS)
+    {
+      atomicAdd(&A.counters[2], c2);
+      atomicAdd(&A.counters[3], c3);
+    }
+  }
+}
+
+/* sum of the split planes, in plane order (deterministic) */
+__global__ void k_sum_planes(const float *__restrict__ planes, int splits, size_t n, float *__restrict__ out)
+{
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float acc = 0.0f;
+  for (int k = 0; k < splits; k++)
+    acc += planes[(size_t)k * n + i];
+  out[i] = acc;
+}
+
+/* raytracer.c:215-220: mean, pow(c, 1/5.0), clamp, truncate.  NaN -> 255 (CLAMP macro). */
+__global__ void k_tonemap(const float *__restrict__ accum, size_t n, double inv_samples, uint8_t *__restrict__ fb)
+{
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  double c = __dmul_rn((double)accum[i], inv_samples);
+  double g = pow(c, __ddiv_rn(1.0, 5.0));
+  double clamped = (g < 1.0) ? g : 1.0; /* MIN(x, 1): NaN -> 1 */
+  clamped = (0.0 > clamped) ? 0.0 : clamped; /* MAX(0, .) */
+  fb[i] = (uint8_t)(__dmul_rn(255.0, clamped));
+}
+
+/* ---- probes ------------------------------------------------------------------------ */
+
+__global__ void k_trace_rays(const __grid_constant__ SceneView sv, const double *__restrict__ rays, size_t n,
+                             int use_bvh, int *__restrict__ ids, long long *__restrict__ prims,
+                             double *__restrict__ ts, double *__restrict__ points, double *__restrict__ normals,
+                             double *__restrict__ uvs)
+{
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  d3 o = d3_make(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]);
+  d3 d = d3_make(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+  HitRec best;
+  TraceStats st = { 0u, 0u };
+  if (use_bvh)
+    closest_hit<false>(sv, o, d, best, st);
+  else
+    closest_hit_bruteforce(sv, o, d, best);
+  bool hit = best.t < 1e300;
+  Surface s;
+  if (hit)
+    s = surface_at(sv, o, d, best, true);
+  ids[i] = hit ? s.object : -1;
+  if (prims) prims[i] = hit ? (long long)best.gid : -1ll;
+  if (ts) ts[i] = hit ? best.t : 0.0;
+  if (points)  { points[3 * i] = hit ? s.point.x : 0; points[3 * i + 1] = hit ? s.point.y : 0; points[3 * i + 2] = hit ? s.point.z : 0; }
+  if (normals) { normals[3 * i] = hit ? s.normal.x : 0; normals[3 * i + 1] = hit ? s.normal.y : 0; normals[3 * i + 2] = hit ? s.normal.z : 0; }
+  if (uvs)     { uvs[2 * i] = hit ? s.u : 0; uvs[2 * i + 1] = hit ? s.v : 0; }
+}
+
+/* the first n_vertices vertices of sample `sample` of every pixel, through the very same
+ * path_begin / closest_hit / path_shade as k_render */
+__global__ void k_path_records(const __grid_constant__ RenderArgs A, int sample, int n_vertices,
+                               int *__restrict__ ids, double *__restrict__ points, double *__restrict__ normals,
+                               double *__restrict__ dists, float *__restrict__ radiance)
+{
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= A.width * A.height)
+    return;
+  int x = pix % A.width, y = pix / A.width;
+  for (int k = 0; k < n_vertices; k++)
+  {
+    ids[(size_t)pix * n_vertices + k] = -2;
+    dists[(size_t)pix * n_vertices + k] = 0.0;
+    for (int c = 0; c < 3; c++)
+    {
+      points[((size_t)pix * n_vertices + k) * 3 + c] = 0.0;
+      normals[((size_t)pix * n_vertices + k) * 3 + c] = 0.0;
+    }
+  }
+  PathState st;
+  path_begin(A, st, x, y, (unsigned)pix, (unsigned)sample);
+  float sr = 0, sg = 0, sb = 0;
+  PathCounters pc = { 0u, 0u };
+  TraceStats ts = { 0u, 0u };
+  int vertex = 0;
+  while (st.alive)
+  {
+    HitRec best;
+    closest_hit<false>(A.sv, st.o, st.d, best, ts);
+    d3 origin = st.o;
+    Surface s;
+    bool hit = best.t < 1e300;
+    path_shade(A, st, best, (unsigned)pix, (unsigned)sample, sr, sg, sb, pc, &s);
+    if (vertex < n_vertices)
+    {
+      size_t r = (size_t)pix * n_vertices + vertex;
+      ids[r] = hit ? s.object : -1;
+      if (hit)
+      {
+        dists[r] = d3_length(d3_sub(s.point, origin));
+        points[3 * r] = s.point.x; points[3 * r + 1] = s.point.y; points[3 * r + 2] = s.point.z;
+        normals[3 * r] = s.normal.x; normals[3 * r + 1] = s.normal.y; normals[3 * r + 2] = s.normal.z;
+      }
+    }
+    vertex++;
+  }
+  if (radiance)
+  {
+    radiance[3 * (size_t)pix] = sr; radiance[3 * (size_t)pix + 1] = sg; radiance[3 * (size_t)pix + 2] = sb;
+  }
+}
+
+__global__ void k_philox(const uint4 *__restrict__ ctr, const uint2 *__restrict__ key, size_t n, uint4 *__restrict__ out)
+{
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = philox4x32_10(ctr[i], key[i]);
+}
+
+/* ---- host entry points ---------------------------------------------------------------- */
+
+static int check_desc(const rtb_render_desc *d)
+{
+  if (!d || d->width < 2 || d->height < 2 || d->sample_end < d->sample_begin || d->max_depth < 0 ||
+      d->max_depth > 255 || (long long)d->width * d->height >= (1ll << 30))
+  {
+    /* width/height 1 divide by zero upstream (quirk Q11) */
+    rtb_set_error("rtb_render_desc: need width,height >= 2, sample_end >= sample_begin, 0 <= max_depth <= 255");
+    return RTB_EINVAL;
+  }
+  if (d->dielectric_mode != RTB_DIELECTRIC_STOCHASTIC)
+  {
+    rtb_set_error("dielectric_mode: only RTB_DIELECTRIC_STOCHASTIC runs on the GPU");
+    return RTB_EINVAL;
+  }
+  return RTB_OK;
+}
+
+static void fill_args(RenderArgs &A, const rtb_scene *scene, const double *camera12, const rtb_render_desc *desc)
+{
+  A.sv = scene->view;
+  for (int k = 0; k < 3; k++)
+  {
+    A.cam.pos[k] = camera12[k];
+    A.cam.horizontal[k] = camera12[3 + k];
+    A.cam.vertical[k] = camera12[6 + k];
+    A.cam.llc[k] = camera12[9 + k];
+  }
+  A.width = desc->width;
+  A.height = desc->height;
+  A.tiles_x = (desc->width + 7) / 8;
+  A.n_tiles = A.tiles_x * ((desc->height + 3) / 4);
+  A.s_begin = desc->sample_begin;
+  A.s_end = desc->sample_end;
+  A.max_depth = desc->max_depth;
+  A.dielectric_mode = desc->dielectric_mode;
+  A.key = make_uint2((unsigned)(desc->seed & 0xFFFFFFFFull), (unsigned)(desc->seed >> 32));
+  A.counters = scene->d_counters;
+}
+
+extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
+                                float *d_accum, void *stream_, rtb_counters *counters)
+{
+  if (!scene || !camera12 || !d_accum)
+  {
+    rtb_set_error("rtb_render_accum: NULL argument");
+    return RTB_EINVAL;
+  }
+  int rc = check_desc(desc);
+  if (rc != RTB_OK)
+    return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RTB_CUDA(cudaSetDevice(scene->device));
+
+  RenderArgs A;
+  fill_args(A, scene, camera12, desc);
+  const int spp = desc->sample_end - desc->sample_begin;
+  const size_t n_px = (size_t)desc->width * desc->height;
+  /* enough threads to fill 148 SMs a few times over even for small frames */
+  const long long want_threads = 148ll * 2048 * 2;
+  int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);
+  splits = std::max(1, std::min(splits, spp));
+  int chunk = spp > 0 ? (spp + splits - 1) / splits : 0;
+  if (chunk > 0)
+    splits = (spp + chunk - 1) / chunk;
+  A.chunk = chunk;
+  A.splits = splits;
+
+  unsigned long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (counters)
+  {
+    RTB_CUDA(cudaEventCreate(&ev0));
+    RTB_CUDA(cudaEventCreate(&ev1));
+    RTB_CUDA(cudaMemsetAsync(scene->d_counters, 0, sizeof(unsigned long long) * 8, stream));
+    RTB_CUDA(cudaEventRecord(ev0, stream));
+  }
+
+  if (spp == 0)
+  {
+    RTB_CUDA(cudaMemsetAsync(d_accum, 0, sizeof(float) * 3 * n_px, stream));
+  }
+  else
+  {
+    if (splits > 1)
+    {
+      size_t need = sizeof(float) * 3 * n_px * splits;
+      if (scene->scratch_bytes < need)
+      {
+        RTB_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(scene->d_scratch);
+        scene->d_scratch = nullptr;
+        scene->scratch_bytes = 0;
+        RTB_CUDA(cudaMalloc(&scene->d_scratch, need));
+        scene->scratch_bytes = need;
+      }
+      A.out = scene->d_scratch;
+    }
+    else
+      A.out = d_accum;
+    const int threads = 128;
+    const long long warps = (long long)A.n_tiles * splits;
+    const int blocks = (int)((warps * 32 + threads - 1) / threads);
+    if (counters)
+      k_render<true><<<blocks, threads, 0, stream>>>(A);
+    else
+      k_render<false><<<blocks, threads, 0, stream>>>(A);
+    RTB_CUDA(cudaGetLastError());
+    launches++;
+    if (splits > 1)
+    {
+      size_t n = 3 * n_px;
+      k_sum_planes<<<(int)((n + 255) / 256), 256, 0, stream>>>(scene->d_scratch, splits, n, d_accum);
+      RTB_CUDA(cudaGetLastError());
+      launches++;
+    }
+  }
+
+  if (counters)
+  {
+    RTB_CUDA(cudaEventRecord(ev1, stream));
+    RTB_CUDA(cudaEventSynchronize(ev1));
+    unsigned long long h[8];
+    RTB_CUDA(cudaMemcpy(h, scene->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    memset(counters, 0, sizeof(*counters));
+    counters->rays = h[0];
+    counters->rays_intersected = h[1];
+    counters->prim_tests = h[2];
+    counters->node_visits = h[3];
+    counters->paths = h[4];
+    counters->launches = launches;
+    RTB_CUDA(cudaEventElapsedTime(&counters->gpu_ms, ev0, ev1));
+    counters->build_ms = scene->info.build_ms;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
+  return RTB_OK;
+}
+
+extern "C" int rtb_tonemap(const float *d_accum, int width, int height, int total_samples, uint8_t *d_fb,
+                           int device, void *stream_)
+{
+  if (!d_accum || !d_fb || width <= 0 || height <= 0 || total_samples <= 0)
+  {
+    rtb_set_error("rtb_tonemap: bad argument");
+    return RTB_EINVAL;
+  }
+  RTB_CUDA(cudaSetDevice(device));
+  size_t n = (size_t)3 * width * height;
+  k_tonemap<<<(int)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(d_accum, n, 1.0 / (double)total_samples, d_fb);
+  RTB_CUDA(cudaGetLastError());
+  return RTB_OK;
+}
+
+extern "C" int rtb_render(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
+                          uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters)
+{
+  if (!scene || !framebuffer)
+  {
+    rtb_set_error("rtb_render: NULL argument");
+    return RTB_EINVAL;
+  }
+  int rc = check_desc(desc);
+  if (rc != RTB_OK)
+    return rc;
+  RTB_CUDA(cudaSetDevice(scene->device));
+  size_t n = (size_t)3 * desc->width * desc->height;
+  float *d_accum = nullptr;
+  uint8_t *d_fb = nullptr;
+  RTB_CUDA(cudaMalloc(&d_accum, sizeof(float) * n));
+  if (cudaMalloc(&d_fb, n) != cudaSuccess)
+  {
+    cudaFree(d_accum);
+    rtb_set_error("rtb_render: cudaMalloc framebuffer failed");
+    return RTB_ECUDA;
+  }
+  rc = rtb_render_accum(scene, camera12, desc, d_accum, nullptr, counters);
+  int spp = desc->sample_end - desc->sample_begin;
+  if (rc == RTB_OK)
+    rc = rtb_tonemap(d_accum, desc->width, desc->height, spp > 0 ? spp : 1, d_fb, scene->device, nullptr);
+  if (rc == RTB_OK)
+  {
+    cudaError_t e = cudaMemcpy(framebuffer, d_fb, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && accum_or_null)
+      e = cudaMemcpy(accum_or_null, d_accum, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess)
+    {
+      rtb_set_error(std::string("rtb_render: ") + cudaGetErrorString(e));
+      rc = RTB_ECUDA;
+    }
+    if (counters)
+      counters->launches += 1;
+  }
+  cudaFree(d_accum);
+  cudaFree(d_fb);
+  return rc;
+}
+
+template <typename T>
+struct Dev
+{
+  T *p = nullptr;
+  ~Dev() { if (p) cudaFree(p); }
+};
+
+extern "C" int rtb_trace_rays(rtb_scene *scene, const double *rays6, size_t n_rays, int use_bvh, int32_t *ids,
+                              int64_t *prims, double *ts, double *points, double *normals, double *uvs)
+{
+  if (!scene || (n_rays && (!rays6 || !ids)))
+  {
+    rtb_set_error("rtb_trace_rays: NULL argument");
+    return RTB_EINVAL;
+  }
+  if (n_rays == 0)
+    return RTB_OK;
+  RTB_CUDA(cudaSetDevice(scene->device));
+  Dev<double> d_rays, d_ts, d_points, d_normals, d_uvs;
+  Dev<int> d_ids;
+  Dev<long long> d_prims;
+  RTB_CUDA(cudaMalloc(&d_rays.p, sizeof(double) * 6 * n_rays));
+  RTB_CUDA(cudaMalloc(&d_ids.p, sizeof(int) * n_rays));
+  RTB_CUDA(cudaMalloc(&d_prims.p, sizeof(long long) * n_rays));
+  RTB_CUDA(cudaMalloc(&d_ts.p, sizeof(double) * n_rays));
+  RTB_CUDA(cudaMalloc(&d_points.p, sizeof(double) * 3 * n_rays));
+  RTB_CUDA(cudaMalloc(&d_normals.p, sizeof(double) * 3 * n_rays));
+  RTB_CUDA(cudaMalloc(&d_uvs.p, sizeof(double) * 2 * n_rays));
+  RTB_CUDA(cudaMemcpy(d_rays.p, rays6, sizeof(double) * 6 * n_rays, cudaMemcpyHostToDevice));
+  k_trace_rays<<<(int)((n_rays + 127) / 128), 128>>>(scene->view, d_rays.p, n_rays, use_bvh, d_ids.p, d_prims.p,
+                                                     d_ts.p, d_points.p, d_normals.p, d_uvs.p);
+  RTB_CUDA(cudaGetLastError());
+  RTB_CUDA(cudaDeviceSynchronize());
+  RTB_CUDA(cudaMemcpy(ids, d_ids.p, sizeof(int) * n_rays, cudaMemcpyDeviceToHost));
+  if (prims) RTB_CUDA(cudaMemcpy(prims, d_prims.p, sizeof(long long) * n_rays, cudaMemcpyDeviceToHost));
+  if (ts) RTB_CUDA(cudaMemcpy(ts, d_ts.p, sizeof(double) * n_rays, cudaMemcpyDeviceToHost));
+  if (points) RTB_CUDA(cudaMemcpy(points, d_points.p, sizeof(double) * 3 * n_rays, cudaMemcpyDeviceToHost));
+  if (normals) RTB_CUDA(cudaMemcpy(normals, d_normals.p, sizeof(double) * 3 * n_rays, cudaMemcpyDeviceToHost));
+  if (uvs) RTB_CUDA(cudaMemcpy(uvs, d_uvs.p, sizeof(double) * 2 * n_rays, cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}
+
+extern "C" int rtb_path_records(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc, int sample,
+                                int n_vertices, int32_t *ids, double *points, double *normals, double *dists,
+                                float *radiance)
+{
+  if (!scene || !camera12 || !ids || !points || !normals || !dists || n_vertices < 1)
+  {
+    rtb_set_error("rtb_path_records: bad argument");
+    return RTB_EINVAL;
+  }
+  int rc = check_desc(desc);
+  if (rc != RTB_OK)
+    return rc;
+  RTB_CUDA(cudaSetDevice(scene->device));
+  RenderArgs A;
+  fill_args(A, scene, camera12, desc);
+  A.chunk = 1;
+  A.splits = 1;
+  A.out = nullptr;
+  size_t n_px = (size_t)desc->width * desc->height, nr = n_px * n_vertices;
+  Dev<int> d_ids;
+  Dev<double> d_points, d_normals, d_dists;
+  Dev<float> d_rad;
+  RTB_CUDA(cudaMalloc(&d_ids.p, sizeof(int) * nr));
+  RTB_CUDA(cudaMalloc(&d_points.p, sizeof(double) * 3 * nr));
+  RTB_CUDA(cudaMalloc(&d_normals.p, sizeof(double) * 3 * nr));
+  RTB_CUDA(cudaMalloc(&d_dists.p, sizeof(double) * nr));
+  RTB_CUDA(cudaMalloc(&d_rad.p, sizeof(float) * 3 * n_px));
+  k_path_records<<<(int)((n_px + 127) / 128), 128>>>(A, sample, n_vertices, d_ids.p, d_points.p, d_normals.p,
+                                                     d_dists.p, d_rad.p);
+  RTB_CUDA(cudaGetLastError());
+  RTB_CUDA(cudaDeviceSynchronize());
+  RTB_CUDA(cudaMemcpy(ids, d_ids.p, sizeof(int) * nr, cudaMemcpyDeviceToHost));
+  RTB_CUDA(cudaMemcpy(points, d_points.p, sizeof(double) * 3 * nr, cudaMemcpyDeviceToHost));
+  RTB_CUDA(cudaMemcpy(normals, d_normals.p, sizeof(double) * 3 * nr, cudaMemcpyDeviceToHost));
+  RTB_CUDA(cudaMemcpy(dists, d_dists.p, sizeof(double) * nr, cudaMemcpyDeviceToHost));
+  if (radiance)
+    RTB_CUDA(cudaMemcpy(radiance, d_rad.p, sizeof(float) * 3 * n_px, cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}
+
+extern "C" int rtb_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, size_t n, uint32_t *out4, int device)
+{
+  if (!ctr4 || !key2 || !out4)
+  {
+    rtb_set_error("rtb_philox4x32_10: NULL argument");
+    return RTB_EINVAL;
+  }
+  if (n == 0)
+    return RTB_OK;
+  RTB_CUDA(cudaSetDevice(device));
+  Dev<uint4> d_ctr, d_out;
+  Dev<uint2> d_key;
+  RTB_CUDA(cudaMalloc(&d_ctr.p, sizeof(uint4) * n));
+  RTB_CUDA(cudaMalloc(&d_out.p, sizeof(uint4) * n));
+  RTB_CUDA(cudaMalloc(&d_key.p, sizeof(uint2) * n));
+  RTB_CUDA(cudaMemcpy(d_ctr.p, ctr4, sizeof(uint4) * n, cudaMemcpyHostToDevice));
+  RTB_CUDA(cudaMemcpy(d_key.p, key2, sizeof(uint2) * n, cudaMemcpyHostToDevice));
+  k_philox<<<(int)((n + 127) / 128), 128>>>(d_ctr.p, d_key.p, n, d_out.p);
+  RTB_CUDA(cudaGetLastError());
+  RTB_CUDA(cudaDeviceSynchronize());
+  RTB_CUDA(cudaMemcpy(out4, d_out.p, sizeof(uint4) * n, cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}

@@ -1,0 +1,833 @@
+/*
+ * rtb_scene.cu -- scene upload, AoS-double -> SoA marshalling and the GPU BVH build.
+ *
+ * Replaces the implicit scene of the reference (the Object[] handed to render(),
+ * raytracer.h:156) and the O(n) loop of intersect() (raytracer.c:393-464) with a
+ * device-resident structure:
+ *   1. the host walks the caller's records once (pointers only), uploads sphere records
+ *      and the raw 40-byte Vertex arrays, and kernels convert them to 48-byte PrimRecs;
+ *   2. LBVH: 63-bit Morton codes of primitive centroids, radix sort (CUB), Karras 2012
+ *      hierarchy, bottom-up box fit, subtrees of <= RTB_LEAF_MAX primitives collapsed to
+ *      leaves, nodes emitted in the 64-byte two-child-box layout the walk wants;
+ *   3. primitives that are far larger than the rest (the r=10000 wall spheres of
+ *      main.c:258-299) are kept out of the tree in a short list tested for every ray:
+ *      their centroids would otherwise stretch the Morton grid until all real geometry
+ *      collapses into a handful of cells.
+ * Boxes are padded so the FP32 walk is conservative w.r.t. the exact double tests (see
+ * rtb_device.cuh and DESIGN.md "Precision").
+ */
+#include "rtb_internal.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cfloat>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+/* ---- error text ------------------------------------------------------------- */
+
+static thread_local std::string g_last_error;
+void rtb_set_error(const std::string &msg) { g_last_error = msg; }
+extern "C" const char *rtb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *rtb_version(void) { return "rtb200 0.1 (sm_100a)"; }
+
+extern "C" int rtb_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess)
+  {
+    rtb_set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  return n;
+}
+
+/* ---- marshalling kernels ------------------------------------------------------ */
+
+struct SphereIn
+{
+  double cx, cy, cz, r;
+  int obj, gid;
+};
+
+__device__ __forceinline__ float4 pack_double2(double a, double b)
+{
+  return make_float4(__int_as_float(__double2loint(a)), __int_as_float(__double2hiint(a)),
+                     __int_as_float(__double2loint(b)), __int_as_float(__double2hiint(b)));
+}
+
+__global__ void k_marshal_spheres(const SphereIn *__restrict__ in, int n, PrimRec *__restrict__ out,
+                                  float4 *__restrict__ box_lo, float4 *__restrict__ box_hi)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  SphereIn s = in[i];
+  PrimRec r;
+  r.a = pack_double2(s.cx, s.cy);
+  r.b = pack_double2(s.cz, s.r);
+  r.c = make_float4(0.0f, __int_as_float(s.gid), __uint_as_float((unsigned)s.obj | RTB_PRIM_SPHERE_BIT), 0.0f);
+  out[i] = r;
+  if (box_lo)
+  {
+    double rr = fabs(s.r);
+    box_lo[i] = make_float4(__double2float_rd(s.cx - rr), __double2float_rd(s.cy - rr), __double2float_rd(s.cz - rr), 0.0f);
+    box_hi[i] = make_float4(__double2float_ru(s.cx + rr), __double2float_ru(s.cy + rr), __double2float_ru(s.cz + rr), 0.0f);
+  }
+}
+
+__global__ void k_marshal_tris(const RefVertex *__restrict__ verts, int n_tris, int obj, int gid_first,
+                               PrimRec *__restrict__ out, float4 *__restrict__ box_lo,
+                               float4 *__restrict__ box_hi, float2 *__restrict__ tex)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tris)
+    return;
+  const double *p = reinterpret_cast<const double *>(verts + 3 * (size_t)i);
+  /* 3 vertices x 5 doubles, contiguous */
+  float v[3][3], t[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+  {
+    v[k][0] = __double2float_rn(p[5 * k + 0]);
+    v[k][1] = __double2float_rn(p[5 * k + 1]);
+    v[k][2] = __double2float_rn(p[5 * k + 2]);
+    t[k][0] = __double2float_rn(p[5 * k + 3]);
+    t[k][1] = __double2float_rn(p[5 * k + 4]);
+  }
+  PrimRec r;
+  r.a = make_float4(v[0][0], v[0][1], v[0][2], v[1][0]);
+  r.b = make_float4(v[1][1], v[1][2], v[2][0], v[2][1]);
+  r.c = make_float4(v[2][2], __int_as_float(gid_first + i), __uint_as_float((unsigned)obj), 0.0f);
+  out[i] = r;
+  box_lo[i] = make_float4(fminf(v[0][0], fminf(v[1][0], v[2][0])), fminf(v[0][1], fminf(v[1][1], v[2][1])),
+                          fminf(v[0][2], fminf(v[1][2], v[2][2])), 0.0f);
+  box_hi[i] = make_float4(fmaxf(v[0][0], fmaxf(v[1][0], v[2][0])), fmaxf(v[0][1], fmaxf(v[1][1], v[2][1])),
+                          fmaxf(v[0][2], fmaxf(v[1][2], v[2][2])), 0.0f);
+  if (tex)
+  {
+    tex[3 * (size_t)i + 0] = make_float2(t[0][0], t[0][1]);
+    tex[3 * (size_t)i + 1] = make_float2(t[1][0], t[1][1]);
+    tex[3 * (size_t)i + 2] = make_float2(t[2][0], t[2][1]);
+  }
+}
+
+/* ---- bounds ------------------------------------------------------------------- */
+
+__device__ __forceinline__ unsigned float_to_ordered(float f)
+{
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float ordered_to_float(unsigned u)
+{
+  unsigned v = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+
+/* bounds[0..2] = min of box_lo, bounds[3..5] = max of box_hi (ordered-uint encoded) */
+__global__ void k_bounds(const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, int n,
+                         unsigned *__restrict__ bounds)
+{
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    float4 a = box_lo[i], b = box_hi[i];
+    lo[0] = fminf(lo[0], a.x); lo[1] = fminf(lo[1], a.y); lo[2] = fminf(lo[2], a.z);
+    hi[0] = fmaxf(hi[0], b.x); hi[1] = fmaxf(hi[1], b.y); hi[2] = fmaxf(hi[2], b.z);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+  {
+    for (int off = 16; off > 0; off >>= 1)
+    {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], off));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], off));
+    }
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+      atomicMin(&bounds[k], float_to_ordered(lo[k]));
+      atomicMax(&bounds[3 + k], float_to_ordered(hi[k]));
+    }
+  }
+}
+
+/* ---- Morton codes --------------------------------------------------------------- */
+
+__device__ __forceinline__ unsigned long long spread21(unsigned v)
+{
+  unsigned long long x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void k_morton(const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, int n,
+                         float3 origin, float3 inv_extent, unsigned long long *__restrict__ keys,
+                         unsigned *__restrict__ vals)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float4 a = box_lo[i], b = box_hi[i];
+  float cx = (0.5f * (a.x + b.x) - origin.x) * inv_extent.x;
+  float cy = (0.5f * (a.y + b.y) - origin.y) * inv_extent.y;
+  float cz = (0.5f * (a.z + b.z) - origin.z) * inv_extent.z;
+  const float scale = 2097151.0f; /* 2^21 - 1 */
+  unsigned qx = (unsigned)fminf(fmaxf(cx * scale, 0.0f), scale);
+  unsigned qy = (unsigned)fminf(fmaxf(cy * scale, 0.0f), scale);
+  unsigned qz = (unsigned)fminf(fmaxf(cz * scale, 0.0f), scale);
+  keys[i] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+  vals[i] = (unsigned)i;
+}
+
+/* ---- Karras 2012 hierarchy ------------------------------------------------------ */
+
+__device__ __forceinline__ int delta(const unsigned long long *__restrict__ keys, int n, int i, int j)
+{
+  if (j < 0 || j >= n)
+    return -1;
+  unsigned long long x = keys[i] ^ keys[j];
+  if (x == 0ull)
+    return 64 + __clz((unsigned)i ^ (unsigned)j);
+  return __clzll((long long)x);
+}
+
+/* child encoding inside the build: >= 0 inner node, < 0 leaf at sorted position ~c */
+__global__ void k_karras(const unsigned long long *__restrict__ keys, int n, int2 *__restrict__ children,
+                         int *__restrict__ parent_inner, int *__restrict__ parent_leaf,
+                         int *__restrict__ range_first)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin)
+    lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin)
+      l += t;
+  int j = i + l * d;
+  int dnode = delta(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do
+  {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode)
+      s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  int left = (lo == gamma) ? ~gamma : gamma;
+  int right = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+  children[i] = make_int2(left, right);
+  range_first[i] = lo;
+  if (left >= 0) parent_inner[left] = i; else parent_leaf[~left] = i;
+  if (right >= 0) parent_inner[right] = i; else parent_leaf[~right] = i;
+  if (i == 0)
+    parent_inner[0] = -1;
+}
+
+/* bottom-up: the second thread to reach a node computes its box and primitive count */
+__global__ void k_fit(const unsigned *__restrict__ vals, const float4 *__restrict__ box_lo,
+                      const float4 *__restrict__ box_hi, int n, const int2 *__restrict__ children,
+                      const int *__restrict__ parent_inner, const int *__restrict__ parent_leaf,
+                      float4 *__restrict__ node_lo, float4 *__restrict__ node_hi, int *__restrict__ flags,
+                      int *__restrict__ max_depth)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int node = parent_leaf[i];
+  while (node >= 0)
+  {
+    __threadfence();
+    if (atomicAdd(&flags[node], 1) == 0)
+      return;
+    __threadfence();
+    int2 ch = children[node];
+    float4 alo, ahi, blo, bhi;
+    int acount, bcount;
+    if (ch.x < 0) { unsigned p = vals[~ch.x]; alo = box_lo[p]; ahi = box_hi[p]; acount = 1; }
+    else { alo = __ldcg(&node_lo[ch.x]); ahi = __ldcg(&node_hi[ch.x]); acount = __float_as_int(alo.w); }
+    if (ch.y < 0) { unsigned p = vals[~ch.y]; blo = box_lo[p]; bhi = box_hi[p]; bcount = 1; }
+    else { blo = __ldcg(&node_lo[ch.y]); bhi = __ldcg(&node_hi[ch.y]); bcount = __float_as_int(blo.w); }
+    float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float(acount + bcount));
+    float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    __stcg(&node_lo[node], lo);
+    __stcg(&node_hi[node], hi);
+    node = parent_inner[node];
+  }
+  (void)max_depth;
+}
+
+__global__ void k_depth(int n, const int *__restrict__ parent_inner, const int *__restrict__ parent_leaf,
+                        int *__restrict__ max_depth)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int depth = 0;
+  for (int node = parent_leaf[i]; node >= 0; node = parent_inner[node])
+    depth++;
+  for (int off = 16; off > 0; off >>= 1)
+    depth = max(depth, __shfl_xor_sync(0xFFFFFFFFu, depth, off));
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(max_depth, depth);
+}
+
+__device__ __forceinline__ int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
+
+/* one traversal node per inner node whose subtree holds more than RTB_LEAF_MAX primitives */
+__global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restrict__ box_lo,
+                       const float4 *__restrict__ box_hi, int n, const int2 *__restrict__ children,
+                       const int *__restrict__ range_first, const float4 *__restrict__ node_lo,
+                       const float4 *__restrict__ node_hi, float pad, float4 *__restrict__ out_nodes,
+                       int *__restrict__ emitted)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  int count = __float_as_int(node_lo[i].w);
+  if (count <= RTB_LEAF_MAX)
+    return;
+  int2 ch = children[i];
+  float4 lo[2], hi[2];
+  int ref[2];
+  int c[2] = { ch.x, ch.y };
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+  {
+    if (c[k] < 0)
+    {
+      unsigned p = vals[~c[k]];
+      lo[k] = box_lo[p];
+      hi[k] = box_hi[p];
+      ref[k] = leaf_ref(~c[k], 1);
+    }
+    else
+    {
+      lo[k] = node_lo[c[k]];
+      hi[k] = node_hi[c[k]];
+      int cc = __float_as_int(lo[k].w);
+      ref[k] = (cc <= RTB_LEAF_MAX) ? leaf_ref(range_first[c[k]], cc) : c[k];
+    }
+  }
+  out_nodes[4 * (size_t)i + 0] = make_float4(lo[0].x - pad, hi[0].x + pad, lo[0].y - pad, hi[0].y + pad);
+  out_nodes[4 * (size_t)i + 1] = make_float4(lo[1].x - pad, hi[1].x + pad, lo[1].y - pad, hi[1].y + pad);
+  out_nodes[4 * (size_t)i + 2] = make_float4(lo[0].z - pad, hi[0].z + pad, lo[1].z - pad, hi[1].z + pad);
+  out_nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.0f, 0.0f);
+  atomicAdd(emitted, 1);
+}
+
+__global__ void k_reorder(const unsigned *__restrict__ vals, int n, const PrimRec *__restrict__ in,
+                          PrimRec *__restrict__ out, const float2 *__restrict__ tex_in, float2 *__restrict__ tex_out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  unsigned p = vals[i];
+  out[i] = in[p];
+  if (tex_in)
+  {
+    tex_out[3 * (size_t)i + 0] = tex_in[3 * (size_t)p + 0];
+    tex_out[3 * (size_t)i + 1] = tex_in[3 * (size_t)p + 1];
+    tex_out[3 * (size_t)i + 2] = tex_in[3 * (size_t)p + 2];
+  }
+}
+
+/* ---- host side ------------------------------------------------------------------- */
+
+namespace
+{
+struct MeshRange
+{
+  const RefVertex *verts;
+  size_t n_tris;
+  int obj;
+  long long gid_first;
+  bool checkered;
+};
+
+struct HostScene
+{
+  std::vector<SphereIn> spheres;
+  std::vector<MeshRange> meshes;
+  std::vector<float4> mats; /* 2 per object */
+  size_t n_objects = 0;
+  long long n_prims = 0;
+};
+
+template <typename T>
+struct DevBuf
+{
+  T *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+  T *release() { T *q = p; p = nullptr; return q; }
+};
+
+void push_material(HostScene &hs, uint32_t flags, const RefVec3 &color, const RefVec3 &emission)
+{
+  /* Russian roulette (raytracer.c:497-502): survive iff u < prob with u = r31 / 2^31, i.e.
+   * iff r31 < ceil(prob * 2^31) -- an integer threshold, so the decision is exact.  The
+   * surviving albedo albedo * (1/prob) is computed in double, then rounded once. */
+  double prob = std::max(color.x, std::max(color.y, color.z)); /* MAX(a.x, MAX(a.y, a.z)) */
+  uint32_t threshold;
+  if (!(prob > 0.0)) threshold = 0u; /* also NaN: `u < NaN` is false upstream */
+  else if (prob >= 1.0) threshold = 0x80000000u;
+  else threshold = (uint32_t)std::ceil(prob * 2147483648.0);
+  double inv = 1 / prob;
+  float ax = (float)(color.x * inv), ay = (float)(color.y * inv), az = (float)(color.z * inv);
+  if (threshold == 0u) ax = ay = az = 0.0f;
+  float4 m0, m1;
+  m0.x = ax; m0.y = ay; m0.z = az;
+  memcpy(&m0.w, &threshold, 4);
+  m1.x = (float)emission.x; m1.y = (float)emission.y; m1.z = (float)emission.z;
+  memcpy(&m1.w, &flags, 4);
+  hs.mats.push_back(m0);
+  hs.mats.push_back(m1);
+}
+
+int gather_scene_objects(const RefSceneObject *objs, size_t n, HostScene &hs)
+{
+  hs.n_objects = n;
+  long long gid = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    const RefSceneObject &o = objs[i];
+    push_material(hs, o.material.flags, o.material.color, o.material.emission);
+    if (o.type == 0)
+    {
+      const RefSphere *s = static_cast<const RefSphere *>(o.geometry);
+      if (!s) { rtb_set_error("sphere object with NULL geometry"); return RTB_EINVAL; }
+      hs.spheres.push_back(SphereIn{ s->center.x, s->center.y, s->center.z, s->radius, (int)i, (int)gid });
+      gid += 1;
+    }
+    else if (o.type == 1)
+    {
+      const RefMesh *m = static_cast<const RefMesh *>(o.geometry);
+      if (!m) { rtb_set_error("mesh object with NULL geometry"); return RTB_EINVAL; }
+      if (m->num_triangles > 0)
+      {
+        if (!m->vertices) { rtb_set_error("mesh with NULL vertices"); return RTB_EINVAL; }
+        hs.meshes.push_back(MeshRange{ m->vertices, m->num_triangles, (int)i, gid,
+                                       (o.material.flags & RT_M_CHECKERED) != 0 });
+        gid += (long long)m->num_triangles;
+      }
+    }
+    else
+    {
+      rtb_set_error("unknown geometry type"); /* raytracer.c:449-453 exits here */
+      return RTB_EINVAL;
+    }
+  }
+  hs.n_prims = gid;
+  if (gid >= (1ll << 27) || n >= (1ull << 30))
+  {
+    rtb_set_error("scene too large (>= 2^27 primitives)");
+    return RTB_EINVAL;
+  }
+  return RTB_OK;
+}
+
+/* pick the oversized spheres (see file header): radius > 32 x the median primitive size,
+ * at most 16 of them, largest first */
+std::vector<char> choose_big(const HostScene &hs)
+{
+  std::vector<char> big(hs.spheres.size(), 0);
+  std::vector<double> sizes;
+  for (const SphereIn &s : hs.spheres)
+    sizes.push_back(std::fabs(s.r));
+  for (const MeshRange &m : hs.meshes)
+  {
+    size_t step = std::max<size_t>(1, m.n_tris / 2048);
+    for (size_t t = 0; t < m.n_tris; t += step)
+    {
+      const RefVertex *v = m.verts + 3 * t;
+      double ext = 0;
+      for (int a = 0; a < 3; a++)
+      {
+        const double *p0 = &v[0].pos.x, *p1 = &v[1].pos.x, *p2 = &v[2].pos.x;
+        double lo = std::min(p0[a], std::min(p1[a], p2[a])), hi = std::max(p0[a], std::max(p1[a], p2[a]));
+        ext = std::max(ext, hi - lo);
+      }
+      /* weight a sampled triangle by the triangles it stands for */
+      for (size_t r = 0; r < std::min<size_t>(step, 64); r++)
+        sizes.push_back(0.5 * ext);
+    }
+  }
+  if (sizes.size() < 2)
+    return big;
+  std::vector<double> sorted = sizes;
+  std::nth_element(sorted.begin(), sorted.begin() + (sorted.size() - 1) / 2, sorted.end());
+  double median = sorted[(sorted.size() - 1) / 2];
+  double threshold = 32.0 * median;
+  std::vector<std::pair<double, size_t>> cand;
+  for (size_t i = 0; i < hs.spheres.size(); i++)
+    if (std::fabs(hs.spheres[i].r) > threshold || !std::isfinite(hs.spheres[i].r))
+      cand.push_back({ std::fabs(hs.spheres[i].r), i });
+  std::sort(cand.begin(), cand.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &b) {
+    return a.first > b.first || (a.first == b.first && a.second < b.second);
+  });
+  for (size_t k = 0; k < cand.size() && k < 16; k++)
+    big[cand[k].second] = 1;
+  return big;
+}
+
+int build_scene(HostScene &hs, int device, rtb_scene **out)
+{
+  int ndev = 0;
+  RTB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+  {
+    rtb_set_error("invalid CUDA device ordinal");
+    return RTB_EINVAL;
+  }
+  RTB_CUDA(cudaSetDevice(device));
+
+  cudaEvent_t ev0, ev1;
+  RTB_CUDA(cudaEventCreate(&ev0));
+  RTB_CUDA(cudaEventCreate(&ev1));
+  RTB_CUDA(cudaEventRecord(ev0, 0));
+
+  std::vector<char> big = choose_big(hs);
+  std::vector<SphereIn> big_spheres, bvh_spheres;
+  for (size_t i = 0; i < hs.spheres.size(); i++)
+    (big[i] ? big_spheres : bvh_spheres).push_back(hs.spheres[i]);
+  /* keep the big list in loop order (cosmetic: ties are resolved by gid anyway) */
+  size_t n_tris = 0;
+  bool want_tex = false;
+  for (const MeshRange &m : hs.meshes)
+  {
+    n_tris += m.n_tris;
+    want_tex = want_tex || m.checkered;
+  }
+  const size_t n_bs = bvh_spheres.size();
+  const size_t N = n_bs + n_tris; /* primitives in the tree */
+
+  struct SceneDeleter { void operator()(rtb_scene *s) const { rtb_scene_destroy(s); } };
+  std::unique_ptr<rtb_scene, SceneDeleter> sc(new rtb_scene());
+  sc->device = device;
+  size_t dev_bytes = 0;
+
+  /* materials */
+  RTB_CUDA(cudaMalloc(&sc->d_mats, sizeof(float4) * std::max<size_t>(2, hs.mats.size())));
+  if (!hs.mats.empty())
+    RTB_CUDA(cudaMemcpy(sc->d_mats, hs.mats.data(), sizeof(float4) * hs.mats.size(), cudaMemcpyHostToDevice));
+  dev_bytes += sizeof(float4) * hs.mats.size();
+  RTB_CUDA(cudaMalloc(&sc->d_counters, sizeof(unsigned long long) * 8));
+
+  /* big list */
+  RTB_CUDA(cudaMalloc(&sc->d_big, sizeof(PrimRec) * std::max<size_t>(1, big_spheres.size())));
+  if (!big_spheres.empty())
+  {
+    DevBuf<SphereIn> d_in;
+    RTB_CUDA(d_in.alloc(big_spheres.size()));
+    RTB_CUDA(cudaMemcpy(d_in.p, big_spheres.data(), sizeof(SphereIn) * big_spheres.size(), cudaMemcpyHostToDevice));
+    k_marshal_spheres<<<1, 32>>>(d_in.p, (int)big_spheres.size(), reinterpret_cast<PrimRec *>(sc->d_big), nullptr, nullptr);
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaDeviceSynchronize());
+  }
+  dev_bytes += sizeof(PrimRec) * big_spheres.size();
+
+  SceneView &view = sc->view;
+  view.n_big = (int)big_spheres.size();
+  view.n_objects = (int)hs.n_objects;
+  view.n_prims = (int)N;
+  view.root_ref = RTB_REF_NONE;
+  view.tex = nullptr;
+  int bvh_depth = 0;
+  size_t n_nodes = 0;
+
+  if (N > 0)
+  {
+    const int T = 256;
+    const int blocks = (int)((N + T - 1) / T);
+    DevBuf<PrimRec> d_unsorted;
+    DevBuf<float4> d_lo, d_hi;
+    DevBuf<float2> d_tex_unsorted;
+    RTB_CUDA(d_unsorted.alloc(N));
+    RTB_CUDA(d_lo.alloc(N));
+    RTB_CUDA(d_hi.alloc(N));
+    if (want_tex)
+    {
+      RTB_CUDA(d_tex_unsorted.alloc(3 * N));
+      RTB_CUDA(cudaMemset(d_tex_unsorted.p, 0, sizeof(float2) * 3 * N));
+    }
+
+    if (n_bs)
+    {
+      DevBuf<SphereIn> d_in;
+      RTB_CUDA(d_in.alloc(n_bs));
+      RTB_CUDA(cudaMemcpy(d_in.p, bvh_spheres.data(), sizeof(SphereIn) * n_bs, cudaMemcpyHostToDevice));
+      k_marshal_spheres<<<(int)((n_bs + T - 1) / T), T>>>(d_in.p, (int)n_bs, d_unsorted.p, d_lo.p, d_hi.p);
+      RTB_CUDA(cudaGetLastError());
+      RTB_CUDA(cudaDeviceSynchronize());
+    }
+    {
+      /* raw Vertex arrays go up as they are (120 B per triangle) and are converted on the
+       * device; staging is bounded so huge meshes do not double their footprint */
+      const size_t chunk_tris = 1u << 20;
+      DevBuf<RefVertex> d_stage;
+      size_t max_chunk = 0;
+      for (const MeshRange &m : hs.meshes)
+        max_chunk = std::max(max_chunk, std::min(chunk_tris, m.n_tris));
+      if (max_chunk)
+        RTB_CUDA(d_stage.alloc(3 * max_chunk));
+      size_t offset = n_bs;
+      for (const MeshRange &m : hs.meshes)
+      {
+        for (size_t t0 = 0; t0 < m.n_tris; t0 += chunk_tris)
+        {
+          size_t cnt = std::min(chunk_tris, m.n_tris - t0);
+          RTB_CUDA(cudaMemcpy(d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, cudaMemcpyHostToDevice));
+          k_marshal_tris<<<(int)((cnt + T - 1) / T), T>>>(d_stage.p, (int)cnt, m.obj, (int)(m.gid_first + (long long)t0),
+                                                          d_unsorted.p + offset, d_lo.p + offset, d_hi.p + offset,
+                                                          want_tex ? d_tex_unsorted.p + 3 * offset : nullptr);
+          RTB_CUDA(cudaGetLastError());
+          RTB_CUDA(cudaDeviceSynchronize());
+          offset += cnt;
+        }
+      }
+    }
+
+    /* scene box of the tree primitives */
+    DevBuf<unsigned> d_bounds;
+    RTB_CUDA(d_bounds.alloc(6));
+    unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+    RTB_CUDA(cudaMemcpy(d_bounds.p, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice));
+    k_bounds<<<std::min(blocks, 1184), T>>>(d_lo.p, d_hi.p, (int)N, d_bounds.p);
+    RTB_CUDA(cudaGetLastError());
+    unsigned hb[6];
+    RTB_CUDA(cudaMemcpy(hb, d_bounds.p, sizeof(hb), cudaMemcpyDeviceToHost));
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++)
+    {
+      lo[k] = ordered_to_float(hb[k]);
+      hi[k] = ordered_to_float(hb[3 + k]);
+    }
+    for (int k = 0; k < 3; k++)
+      if (!std::isfinite(lo[k]) || !std::isfinite(hi[k]))
+      {
+        rtb_set_error("non-finite geometry");
+        return RTB_EINVAL;
+      }
+    double diag = std::sqrt((double)(hi[0] - lo[0]) * (hi[0] - lo[0]) + (double)(hi[1] - lo[1]) * (hi[1] - lo[1]) +
+                            (double)(hi[2] - lo[2]) * (hi[2] - lo[2]));
+    if (diag <= 0) diag = 1e-3;
+    double max_abs = 0;
+    for (int k = 0; k < 3; k++)
+    {
+      view.guard_lo[k] = (float)(lo[k] - diag);
+      view.guard_hi[k] = (float)(hi[k] + diag);
+      max_abs = std::max(max_abs, std::max(std::fabs((double)view.guard_lo[k]), std::fabs((double)view.guard_hi[k])));
+    }
+    /* padding that covers float rounding of the (re-based) ray and of the slab arithmetic:
+     * 2^-20 * (largest origin coordinate + longest parametric distance inside the guard box) */
+    float pad = (float)((max_abs + 3.0 * diag * 1.7320508) * (1.0 / 1048576.0));
+
+    if (N <= RTB_LEAF_MAX)
+    {
+      /* a single leaf; order = insertion order */
+      RTB_CUDA(cudaMalloc(&sc->d_prims, sizeof(PrimRec) * N));
+      RTB_CUDA(cudaMemcpy(sc->d_prims, d_unsorted.p, sizeof(PrimRec) * N, cudaMemcpyDeviceToDevice));
+      if (want_tex)
+      {
+        RTB_CUDA(cudaMalloc(&sc->d_tex, sizeof(float2) * 3 * N));
+        RTB_CUDA(cudaMemcpy(sc->d_tex, d_tex_unsorted.p, sizeof(float2) * 3 * N, cudaMemcpyDeviceToDevice));
+      }
+      RTB_CUDA(cudaMalloc(&sc->d_nodes, sizeof(BvhNode)));
+      view.root_ref = ~(((0) << 3) | ((int)N - 1));
+      bvh_depth = 0;
+    }
+    else
+    {
+      DevBuf<unsigned long long> d_keys, d_keys_sorted;
+      DevBuf<unsigned> d_vals, d_vals_sorted;
+      RTB_CUDA(d_keys.alloc(N));
+      RTB_CUDA(d_keys_sorted.alloc(N));
+      RTB_CUDA(d_vals.alloc(N));
+      RTB_CUDA(d_vals_sorted.alloc(N));
+      float3 origin = make_float3(lo[0], lo[1], lo[2]);
+      /* cubic Morton cells: one scale for all axes (flat scenes keep their resolution) */
+      float max_extent = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+      float inv = max_extent > 0.0f ? 1.0f / max_extent : 0.0f;
+      float3 inv_extent = make_float3(inv, inv, inv);
+      k_morton<<<blocks, T>>>(d_lo.p, d_hi.p, (int)N, origin, inv_extent, d_keys.p, d_vals.p);
+      RTB_CUDA(cudaGetLastError());
+      size_t temp_bytes = 0;
+      RTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p,
+                                               d_vals_sorted.p, (int)N, 0, 63));
+      DevBuf<unsigned char> d_temp;
+      RTB_CUDA(d_temp.alloc(temp_bytes));
+      RTB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p,
+                                               d_vals_sorted.p, (int)N, 0, 63));
+
+      DevBuf<int2> d_children;
+      DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc;
+      DevBuf<float4> d_node_lo, d_node_hi;
+      RTB_CUDA(d_children.alloc(N - 1));
+      RTB_CUDA(d_parent_inner.alloc(N - 1));
+      RTB_CUDA(d_parent_leaf.alloc(N));
+      RTB_CUDA(d_first.alloc(N - 1));
+      RTB_CUDA(d_flags.alloc(N - 1));
+      RTB_CUDA(d_misc.alloc(2));
+      RTB_CUDA(d_node_lo.alloc(N - 1));
+      RTB_CUDA(d_node_hi.alloc(N - 1));
+      RTB_CUDA(cudaMemset(d_flags.p, 0, sizeof(int) * (N - 1)));
+      RTB_CUDA(cudaMemset(d_misc.p, 0, sizeof(int) * 2));
+      k_karras<<<blocks, T>>>(d_keys_sorted.p, (int)N, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_first.p);
+      RTB_CUDA(cudaGetLastError());
+      k_fit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_parent_inner.p,
+                           d_parent_leaf.p, d_node_lo.p, d_node_hi.p, d_flags.p, d_misc.p);
+      RTB_CUDA(cudaGetLastError());
+      k_depth<<<blocks, T>>>((int)N, d_parent_inner.p, d_parent_leaf.p, d_misc.p);
+      RTB_CUDA(cudaGetLastError());
+
+      RTB_CUDA(cudaMalloc(&sc->d_nodes, sizeof(BvhNode) * (N - 1)));
+      RTB_CUDA(cudaMemset(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1)));
+      k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
+                            d_node_hi.p, pad, sc->d_nodes, d_misc.p + 1);
+      RTB_CUDA(cudaGetLastError());
+      RTB_CUDA(cudaMalloc(&sc->d_prims, sizeof(PrimRec) * N));
+      if (want_tex)
+        RTB_CUDA(cudaMalloc(&sc->d_tex, sizeof(float2) * 3 * N));
+      k_reorder<<<blocks, T>>>(d_vals_sorted.p, (int)N, d_unsorted.p, reinterpret_cast<PrimRec *>(sc->d_prims),
+                               want_tex ? d_tex_unsorted.p : nullptr, sc->d_tex);
+      RTB_CUDA(cudaGetLastError());
+      int misc[2];
+      RTB_CUDA(cudaMemcpy(misc, d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost));
+      bvh_depth = misc[0];
+      n_nodes = (size_t)misc[1];
+      if (bvh_depth > RTB_STACK_SIZE - 2)
+      {
+        rtb_set_error("BVH deeper than the traversal stack");
+        return RTB_EINVAL;
+      }
+      view.root_ref = 0;
+      dev_bytes += sizeof(BvhNode) * (N - 1);
+    }
+    dev_bytes += sizeof(PrimRec) * N + (want_tex ? sizeof(float2) * 3 * N : 0);
+  }
+  else
+  {
+    RTB_CUDA(cudaMalloc(&sc->d_prims, sizeof(PrimRec)));
+    RTB_CUDA(cudaMalloc(&sc->d_nodes, sizeof(BvhNode)));
+    for (int k = 0; k < 3; k++)
+    {
+      view.guard_lo[k] = -FLT_MAX;
+      view.guard_hi[k] = FLT_MAX;
+    }
+  }
+  RTB_CUDA(cudaDeviceSynchronize());
+  RTB_CUDA(cudaEventRecord(ev1, 0));
+  RTB_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0;
+  RTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+
+  view.nodes = sc->d_nodes;
+  view.prims = sc->d_prims;
+  view.big = sc->d_big;
+  view.mats = sc->d_mats;
+  view.tex = sc->d_tex;
+
+  sc->info.n_objects = hs.n_objects;
+  sc->info.n_spheres = hs.spheres.size();
+  sc->info.n_triangles = n_tris;
+  sc->info.n_bvh_prims = N;
+  sc->info.n_bvh_nodes = n_nodes;
+  sc->info.n_big_prims = big_spheres.size();
+  sc->info.device_bytes = dev_bytes;
+  sc->info.build_ms = ms;
+  sc->info.bvh_depth = bvh_depth;
+  sc->info.device = device;
+  *out = sc.release();
+  return RTB_OK;
+}
+} // namespace
+
+extern "C" int rtb_scene_create(const void *scene_objects96, size_t n_objects, int device, rtb_scene **out)
+{
+  if (!out || (n_objects && !scene_objects96))
+  {
+    rtb_set_error("rtb_scene_create: NULL argument");
+    return RTB_EINVAL;
+  }
+  *out = nullptr;
+  HostScene hs;
+  int rc = gather_scene_objects(static_cast<const RefSceneObject *>(scene_objects96), n_objects, hs);
+  if (rc != RTB_OK)
+    return rc;
+  return build_scene(hs, device, out);
+}
+
+extern "C" int rtb_scene_create_objects(const void *objects88, size_t n_objects, int device, rtb_scene **out)
+{
+  if (!out || (n_objects && !objects88))
+  {
+    rtb_set_error("rtb_scene_create_objects: NULL argument");
+    return RTB_EINVAL;
+  }
+  *out = nullptr;
+  if (n_objects >= (1ull << 27))
+  {
+    rtb_set_error("scene too large (>= 2^27 primitives)");
+    return RTB_EINVAL;
+  }
+  const RefObject *objs = static_cast<const RefObject *>(objects88);
+  HostScene hs;
+  hs.n_objects = n_objects;
+  hs.n_prims = (long long)n_objects;
+  for (size_t i = 0; i < n_objects; i++)
+  {
+    push_material(hs, objs[i].flags, objs[i].color, objs[i].emission);
+    hs.spheres.push_back(SphereIn{ objs[i].center.x, objs[i].center.y, objs[i].center.z, objs[i].radius, (int)i, (int)i });
+  }
+  return build_scene(hs, device, out);
+}
+
+extern "C" int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info)
+{
+  if (!scene || !info)
+  {
+    rtb_set_error("rtb_scene_info_get: NULL argument");
+    return RTB_EINVAL;
+  }
+  *info = scene->info;
+  return RTB_OK;
+}
+
+extern "C" void rtb_scene_destroy(rtb_scene *scene)
+{
+  if (!scene)
+    return;
+  cudaSetDevice(scene->device);
+  cudaFree(scene->d_nodes);
+  cudaFree(scene->d_prims);
+  cudaFree(scene->d_big);
+  cudaFree(scene->d_mats);
+  cudaFree(scene->d_tex);
+  cudaFree(scene->d_scratch);
+  cudaFree(scene->d_counters);
+  delete scene;
+}
