@@ -518,7 +518,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   for (const MeshRange &m : hs.meshes)
   {
     n_tris += m.n_tris;
-    want_tex = want_tex || m.checkered;
+    want_tex = true; /* texcoords ride along with every mesh (24 B/triangle, only read for M_CHECKERED) */
   }
   const size_t n_bs = bvh_spheres.size();
   const size_t N = n_bs + n_tris; /* primitives in the tree */
