@@ -62,7 +62,7 @@ typedef struct
   int max_depth;                /* run-time MAX_DEPTH (raytracer.h:25); path dies at depth > max_depth */
   int dielectric_mode;          /* RTB_DIELECTRIC_* */
   uint64_t seed;                /* Philox key */
-  int kernel;                   /* 0 = auto, 1 = megakernel, 2 = wavefront */
+  int kernel;                   /* 0 = auto, 1 = megakernel, 2 = warp-scheduled state machine, 3 = megakernel + FP32 pre-test */
   int reserved;
 } rtb_render_desc;
 

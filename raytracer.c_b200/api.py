@@ -220,13 +220,14 @@ def render(objects, camera, width, height, samples):
 
 # ---- the C ABI ----------------------------------------------------------------------------
 
-def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED):
+def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0):
     d = abi.RtbRenderDesc()
     d.width, d.height = width, height
     d.sample_begin, d.sample_end = sample_begin, sample_end
     d.max_depth = max_depth
     d.dielectric_mode = 0
     d.seed = seed
+    d.kernel = kernel
     return d
 
 
@@ -298,7 +299,7 @@ class Scene:
         out = dict(ids=np.zeros(n, np.int32), prims=np.zeros(n, np.int64), t=np.zeros(n, np.float64),
                    points=np.zeros((n, 3), np.float64), normals=np.zeros((n, 3), np.float64),
                    uvs=np.zeros((n, 2), np.float64))
-        _check(self._cu.rtb_trace_rays(self._h, rays.ctypes.data, n, 1 if use_bvh else 0, out["ids"].ctypes.data,
+        _check(self._cu.rtb_trace_rays(self._h, rays.ctypes.data, n, int(use_bvh), out["ids"].ctypes.data,
                                        out["prims"].ctypes.data, out["t"].ctypes.data, out["points"].ctypes.data,
                                        out["normals"].ctypes.data, out["uvs"].ctypes.data), "rtb_trace_rays")
         return out

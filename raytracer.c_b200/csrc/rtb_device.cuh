@@ -189,147 +189,221 @@ __device__ __forceinline__ void test_prim(const PrimView &p, int slot, const d3 
   }
 }
 
-/* ---- nearest hit: big list + FP32 BVH walk with exact leaf tests ------------ */
+/* ---- conservative FP32 sphere pre-test -----------------------------------------
+ * Decides, in FP32 with explicit error bounds, that the exact double test cannot produce a
+ * hit that beats `best`: either the reference's test certainly returns false (tca < 0 or
+ * d2 > r2, raytracer.c:84-89) or even a lower bound of its t exceeds best.t.  Never rejects
+ * a primitive the exact test would accept as the new nearest hit (ties included), so the
+ * result of the query is unchanged; it only saves FP64 work.
+ * Error model: every coordinate entering the test is rounded to float (relative 2^-24);
+ * A = |c|_1 + r + |o|_1 bounds every intermediate magnitude, linear quantities (L, tca) are
+ * off by at most e = A*2^-20, quadratic ones (d2, r2-d2) by at most eq = 10*A*A*2^-20. */
+__device__ __forceinline__ bool sphere_may_win(const PrimView &p, float ofx, float ofy, float ofz, float dfx,
+                                               float dfy, float dfz, float o_abs1, float best_t_up)
+{
+  float cx = (float)p.cx(), cy = (float)p.cy(), cz = (float)p.cz(), r = (float)p.radius();
+  float A = (fabsf(cx) + fabsf(cy) + fabsf(cz) + fabsf(r) + o_abs1) * 1.0000005f;
+  float e = A * 9.5367431640625e-07f;            /* 2^-20 */
+  float eq = 10.0f * A * e;
+  float Lx = cx - ofx, Ly = cy - ofy, Lz = cz - ofz;
+  float tca = fmaf(Lz, dfz, fmaf(Ly, dfy, Lx * dfx));
+  if (tca < -e)
+    return false;
+  float d2 = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx)) - tca * tca;
+  float disc = fmaf(r, r, -d2);
+  if (disc < -eq)
+    return false;
+  float thc_hi = sqrtf(fmaxf(disc + eq, 0.0f)) * 1.000001f;
+  float t_lo = tca - e - thc_hi;                 /* lower bound of the near root */
+  return !(t_lo > best_t_up);
+}
+
+template <bool FILTER>
+__device__ __forceinline__ void test_prim_filtered(const PrimView &p, int slot, const d3 &o, const d3 &d,
+                                                   float ofx, float ofy, float ofz, float dfx, float dfy, float dfz,
+                                                   float o_abs1, HitRec &best, unsigned &exact_tests)
+{
+  if (FILTER && p.is_sphere())
+  {
+    float best_up = best.t >= 1e30 ? 3.0e38f : __double2float_ru(best.t) * 1.0000005f;
+    if (!sphere_may_win(p, ofx, ofy, ofz, dfx, dfy, dfz, o_abs1, best_up))
+      return;
+  }
+  exact_tests++;
+  test_prim(p, slot, o, d, best);
+}
+
+/* ---- nearest hit: big list + FP32 BVH walk with exact leaf tests ------------
+ * The pieces below are shared by the simple per-ray loop (closest_hit, used by the probes)
+ * and by the warp-scheduled state machine of k_render. */
 
 struct TraceStats
 {
   unsigned prim_tests, node_visits;
 };
 
-template <bool STATS>
+/* the FP32 view of a ray used by the walk */
+struct RayF
+{
+  float dfx, dfy, dfz;    /* direction rounded to float (for the sphere pre-test) */
+  float ofx, ofy, ofz;    /* ORIGINAL origin rounded to float (sphere pre-test) */
+  float idx, idy, idz;    /* 1/direction, zero components replaced by +-tiny */
+  float oodx, oody, oodz; /* (re-based origin) * idir */
+  float o_abs1;           /* |o|_1 of the original origin */
+  float tmax;             /* walk bound in the re-based frame */
+  double t_base;          /* parametric offset of the re-based origin */
+};
+
+#define RTB_WIDEN 1.0000005f /* > (1+2^-23)^4: slab arithmetic rounding */
+
+__device__ __forceinline__ void rayf_basic(const d3 &o, const d3 &d, RayF &rf)
+{
+  rf.ofx = (float)o.x; rf.ofy = (float)o.y; rf.ofz = (float)o.z;
+  rf.dfx = (float)d.x; rf.dfy = (float)d.y; rf.dfz = (float)d.z;
+  rf.o_abs1 = fabsf(rf.ofx) + fabsf(rf.ofy) + fabsf(rf.ofz);
+}
+
+/* Prepares the walk.  Returns false if the ray cannot touch the tree (no primitives, or it
+ * misses the guard box).  If the origin lies outside the guard box the ray is first
+ * advanced (in double) to just before its entry point so that float rounding of the origin
+ * stays within the padding the boxes were built with. */
+__device__ __forceinline__ bool rayf_walk_setup(const SceneView &sv, const d3 &o, const d3 &d, const HitRec &best, RayF &rf)
+{
+  if (sv.n_prims == 0)
+    return false;
+  float ofx = rf.ofx, ofy = rf.ofy, ofz = rf.ofz;
+  float dfx = rf.dfx, dfy = rf.dfy, dfz = rf.dfz;
+  const float tiny = 1e-24f;
+  if (fabsf(dfx) < tiny) dfx = copysignf(tiny, dfx);
+  if (fabsf(dfy) < tiny) dfy = copysignf(tiny, dfy);
+  if (fabsf(dfz) < tiny) dfz = copysignf(tiny, dfz);
+  rf.idx = 1.0f / dfx; rf.idy = 1.0f / dfy; rf.idz = 1.0f / dfz;
+  rf.t_base = 0.0;
+  bool outside = ofx < sv.guard_lo[0] || ofx > sv.guard_hi[0] || ofy < sv.guard_lo[1] ||
+                 ofy > sv.guard_hi[1] || ofz < sv.guard_lo[2] || ofz > sv.guard_hi[2];
+  if (outside)
+  {
+    float ax = (sv.guard_lo[0] - ofx) * rf.idx, bx = (sv.guard_hi[0] - ofx) * rf.idx;
+    float ay = (sv.guard_lo[1] - ofy) * rf.idy, by = (sv.guard_hi[1] - ofy) * rf.idy;
+    float az = (sv.guard_lo[2] - ofz) * rf.idz, bz = (sv.guard_hi[2] - ofz) * rf.idz;
+    float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    float t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    /* the guard box is far larger than the padded scene box, so this rough FP32 test
+     * cannot reject a ray that touches the scene box */
+    if (t_out < 0.0f || t_in > t_out * 1.001f + 1e-3f)
+      return false;
+    if (t_in > 0.0f)
+    {
+      rf.t_base = (double)(t_in * 0.999f);
+      ofx = (float)fma(d.x, rf.t_base, o.x);
+      ofy = (float)fma(d.y, rf.t_base, o.y);
+      ofz = (float)fma(d.z, rf.t_base, o.z);
+    }
+  }
+  rf.oodx = ofx * rf.idx; rf.oody = ofy * rf.idy; rf.oodz = ofz * rf.idz;
+  rf.tmax = (best.t >= 1e30) ? 3.0e38f : __double2float_ru(best.t - rf.t_base) * RTB_WIDEN;
+  return true;
+}
+
+__device__ __forceinline__ void rayf_update_tmax(RayF &rf, const HitRec &best)
+{
+  if (best.t < 1e30)
+    rf.tmax = __double2float_ru(best.t - rf.t_base) * RTB_WIDEN;
+}
+
+/* One inner node: tests both children, returns the reference to continue with
+ * (RTB_REF_NONE if neither is hit) and pushes the farther one. */
+__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, int *stack_ref,
+                                         float *stack_t, int &sp)
+{
+  const float4 n0 = __ldg(sv.nodes + 4 * cur + 0);
+  const float4 n1 = __ldg(sv.nodes + 4 * cur + 1);
+  const float4 n2 = __ldg(sv.nodes + 4 * cur + 2);
+  const float4 n3 = __ldg(sv.nodes + 4 * cur + 3);
+
+  float c0lx = fmaf(n0.x, rf.idx, -rf.oodx), c0hx = fmaf(n0.y, rf.idx, -rf.oodx);
+  float c0ly = fmaf(n0.z, rf.idy, -rf.oody), c0hy = fmaf(n0.w, rf.idy, -rf.oody);
+  float c0lz = fmaf(n2.x, rf.idz, -rf.oodz), c0hz = fmaf(n2.y, rf.idz, -rf.oodz);
+  float c1lx = fmaf(n1.x, rf.idx, -rf.oodx), c1hx = fmaf(n1.y, rf.idx, -rf.oodx);
+  float c1ly = fmaf(n1.z, rf.idy, -rf.oody), c1hy = fmaf(n1.w, rf.idy, -rf.oody);
+  float c1lz = fmaf(n2.z, rf.idz, -rf.oodz), c1hz = fmaf(n2.w, rf.idz, -rf.oodz);
+
+  float c0min = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.0f));
+  float c0max = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fminf(fmaxf(c0lz, c0hz), rf.tmax));
+  float c1min = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.0f));
+  float c1max = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fminf(fmaxf(c1lz, c1hz), rf.tmax));
+
+  bool h0 = c0min <= c0max * RTB_WIDEN;
+  bool h1 = c1min <= c1max * RTB_WIDEN;
+  int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+  if (h0 && h1)
+  {
+    bool swap = c1min < c0min;
+    stack_ref[sp] = swap ? r0 : r1;
+    stack_t[sp] = swap ? c0min : c1min;
+    sp++;
+    return swap ? r1 : r0;
+  }
+  if (h0) return r0;
+  if (h1) return r1;
+  return RTB_REF_NONE;
+}
+
+/* pop the next subtree that can still contain a nearer hit; RTB_REF_NONE when done */
+__device__ __forceinline__ int stack_pop(const RayF &rf, const int *stack_ref, const float *stack_t, int &sp)
+{
+  while (sp > 0)
+  {
+    sp--;
+    if (stack_t[sp] <= rf.tmax)
+      return stack_ref[sp];
+  }
+  return RTB_REF_NONE;
+}
+
+template <bool STATS, bool FILTER>
 __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best,
                                             TraceStats &st)
 {
   best.t = DBL_MAX;
   best.gid = 0x7FFFFFFF;
   best.slot = 0;
-  bool found_any = false;
-  (void)found_any;
+  RayF rf;
+  rayf_basic(o, d, rf);
+  unsigned exact = 0;
 
-  /* oversized primitives (the r=10000 wall spheres): tested for every ray, exactly */
+  /* oversized primitives (the r=10000 wall spheres): candidates for every ray */
   for (int k = 0; k < sv.n_big; k++)
-  {
-    PrimView p = load_prim(sv.big, k);
-    test_prim(p, ~k, o, d, best);
-    if (STATS) st.prim_tests++;
-  }
-  if (sv.n_prims == 0)
-    return;
+    test_prim_filtered<FILTER>(load_prim(sv.big, k), ~k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy, rf.dfz, rf.o_abs1, best, exact);
 
-  /* FP32 ray for the walk.  If the origin lies outside the guard box the ray is first
-   * advanced (in double) to just before its entry point so that float rounding of the
-   * origin stays within the padding the boxes were built with. */
-  float ofx = (float)o.x, ofy = (float)o.y, ofz = (float)o.z;
-  float dfx = (float)d.x, dfy = (float)d.y, dfz = (float)d.z;
-  const float tiny = 1e-24f;
-  if (fabsf(dfx) < tiny) dfx = copysignf(tiny, dfx);
-  if (fabsf(dfy) < tiny) dfy = copysignf(tiny, dfy);
-  if (fabsf(dfz) < tiny) dfz = copysignf(tiny, dfz);
-  float idx = 1.0f / dfx, idy = 1.0f / dfy, idz = 1.0f / dfz;
-  double t_base = 0.0;
+  if (rayf_walk_setup(sv, o, d, best, rf))
   {
-    bool outside = ofx < sv.guard_lo[0] || ofx > sv.guard_hi[0] || ofy < sv.guard_lo[1] ||
-                   ofy > sv.guard_hi[1] || ofz < sv.guard_lo[2] || ofz > sv.guard_hi[2];
-    if (outside)
+    int stack_ref[RTB_STACK_SIZE];
+    float stack_t[RTB_STACK_SIZE];
+    int sp = 0;
+    int cur = sv.root_ref;
+    while (cur != RTB_REF_NONE)
     {
-      float ax = (sv.guard_lo[0] - ofx) * idx, bx = (sv.guard_hi[0] - ofx) * idx;
-      float ay = (sv.guard_lo[1] - ofy) * idy, by = (sv.guard_hi[1] - ofy) * idy;
-      float az = (sv.guard_lo[2] - ofz) * idz, bz = (sv.guard_hi[2] - ofz) * idz;
-      float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-      float t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-      /* the guard box is far larger than the padded scene box, so this rough FP32 test
-       * cannot reject a ray that touches the scene box */
-      if (t_out < 0.0f || t_in > t_out * 1.001f + 1e-3f)
-        return;
-      if (t_in > 0.0f)
+      if (cur >= 0)
       {
-        t_base = (double)(t_in * 0.999f);
-        ofx = (float)fma(d.x, t_base, o.x);
-        ofy = (float)fma(d.y, t_base, o.y);
-        ofz = (float)fma(d.z, t_base, o.z);
+        if (STATS) st.node_visits++;
+        cur = node_step(sv, rf, cur, stack_ref, stack_t, sp);
+        if (cur != RTB_REF_NONE)
+          continue;
       }
+      else
+      {
+        int code = ~cur;
+        int first = code >> 3, count = (code & 7) + 1;
+        for (int k = 0; k < count; k++)
+          test_prim_filtered<FILTER>(load_prim(sv.prims, first + k), first + k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx,
+                             rf.dfy, rf.dfz, rf.o_abs1, best, exact);
+        rayf_update_tmax(rf, best);
+      }
+      cur = stack_pop(rf, stack_ref, stack_t, sp);
     }
   }
-  const float oodx = ofx * idx, oody = ofy * idy, oodz = ofz * idz;
-  const float widen = 1.0000005f; /* > (1+2^-23)^4: slab arithmetic rounding */
-
-  /* upper bound of the parametric distance still worth visiting, in the re-based FP32 frame */
-  float tmax = (best.t >= 1e30) ? 3.0e38f : __double2float_ru((best.t - t_base)) * widen;
-
-  int stack_ref[RTB_STACK_SIZE];
-  float stack_t[RTB_STACK_SIZE];
-  int sp = 0;
-  int cur = sv.root_ref;
-
-  while (true)
-  {
-    if (cur >= 0)
-    {
-      if (STATS) st.node_visits++;
-      const float4 n0 = __ldg(sv.nodes + 4 * cur + 0);
-      const float4 n1 = __ldg(sv.nodes + 4 * cur + 1);
-      const float4 n2 = __ldg(sv.nodes + 4 * cur + 2);
-      const float4 n3 = __ldg(sv.nodes + 4 * cur + 3);
-
-      float c0lx = fmaf(n0.x, idx, -oodx), c0hx = fmaf(n0.y, idx, -oodx);
-      float c0ly = fmaf(n0.z, idy, -oody), c0hy = fmaf(n0.w, idy, -oody);
-      float c0lz = fmaf(n2.x, idz, -oodz), c0hz = fmaf(n2.y, idz, -oodz);
-      float c1lx = fmaf(n1.x, idx, -oodx), c1hx = fmaf(n1.y, idx, -oodx);
-      float c1ly = fmaf(n1.z, idy, -oody), c1hy = fmaf(n1.w, idy, -oody);
-      float c1lz = fmaf(n2.z, idz, -oodz), c1hz = fmaf(n2.w, idz, -oodz);
-
-      float c0min = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.0f));
-      float c0max = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fminf(fmaxf(c0lz, c0hz), tmax));
-      float c1min = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.0f));
-      float c1max = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fminf(fmaxf(c1lz, c1hz), tmax));
-
-      bool h0 = c0min <= c0max * widen;
-      bool h1 = c1min <= c1max * widen;
-      int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-
-      if (h0 && h1)
-      {
-        bool swap = c1min < c0min;
-        int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
-        float far_t = swap ? c0min : c1min;
-        stack_ref[sp] = far_ref;
-        stack_t[sp] = far_t;
-        sp++;
-        cur = near_ref;
-        continue;
-      }
-      if (h0) { cur = r0; continue; }
-      if (h1) { cur = r1; continue; }
-    }
-    else
-    {
-      /* leaf: exact double tests */
-      int code = ~cur;
-      int first = code >> 3, count = (code & 7) + 1;
-      for (int k = 0; k < count; k++)
-      {
-        PrimView p = load_prim(sv.prims, first + k);
-        test_prim(p, first + k, o, d, best);
-      }
-      if (STATS) st.prim_tests += count;
-      if (best.t < 1e30)
-        tmax = __double2float_ru(best.t - t_base) * widen;
-    }
-    /* pop, skipping subtrees that start beyond the current best */
-    bool got = false;
-    while (sp > 0)
-    {
-      sp--;
-      if (stack_t[sp] <= tmax)
-      {
-        cur = stack_ref[sp];
-        got = true;
-        break;
-      }
-    }
-    if (!got)
-      break;
-  }
+  if (STATS) st.prim_tests += exact;
 }
 
 /* brute force over every primitive: the reference's own O(n) loop (raytracer.c:401-456),

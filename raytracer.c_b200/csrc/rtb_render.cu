@@ -165,7 +165,7 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
   }
 }
 
-template <bool STATS>
+template <bool STATS, bool FILTER>
 __global__ void __launch_bounds__(128) k_render(const __grid_constant__ RenderArgs A)
 {
   const int lane = threadIdx.x & 31;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ RenderAr
       HitRec best;
       pc.rays++;
       pc.rays_hit++;
-      closest_hit<STATS>(A.sv, st.o, st.d, best, ts);
+      closest_hit<STATS, FILTER>(A.sv, st.o, st.d, best, ts);
       path_shade(A, st, best, pixel, (unsigned)s, sr, sg, sb, pc, nullptr);
       if (!st.alive)
         s++;
@@ -219,6 +219,199 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ RenderAr
   }
 
   /* counters: warp reduce, one atomic per warp and counter */
+  unsigned long long c0 = pc.rays, c1 = pc.rays_hit, c2 = ts.prim_tests, c3 = ts.node_visits, c4 = paths;
+  for (int off = 16; off > 0; off >>= 1)
+  {
+    c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, off);
+    c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, off);
+    c4 += __shfl_xor_sync(0xFFFFFFFFu, c4, off);
+    if (STATS)
+    {
+      c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, off);
+      c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, off);
+    }
+  }
+  if (lane == 0)
+  {
+    atomicAdd(&A.counters[0], c0);
+    atomicAdd(&A.counters[1], c1);
+    atomicAdd(&A.counters[4], c4);
+    if (STATS)
+    {
+      atomicAdd(&A.counters[2], c2);
+      atomicAdd(&A.counters[3], c3);
+    }
+  }
+}
+
+/* ---- the production kernel: warp-scheduled state machine ---------------------------------
+ * Same per-lane work as k_render, different control flow.  Profiling k_render on the
+ * 1M-triangle scene (profiles/r1_c3_megakernel.md) showed 4.95 active lanes per issued
+ * instruction: lanes sat idle while a few neighbours ran the long FP64 leaf tests or the
+ * shading code.  Here every lane is in one of three states and each loop iteration the WARP
+ * picks, by ballot, the state most lanes are in and executes only that block:
+ *   NODE   walk inner BVH nodes (FP32 slab tests), a short burst per turn
+ *   PRIM   one candidate primitive: FP32 pre-test, then the exact FP64 test
+ *   SHADE  path_shade (Russian roulette, scatter), next sample, next ray set-up
+ * Lanes in the other states wait for their turn, so the expensive blocks run with many
+ * lanes active instead of one or two.  Progress is guaranteed: the chosen class is never
+ * empty and every step of a class moves its lanes towards SHADE/IDLE. */
+#ifndef RTB_NODE_BURST
+#define RTB_NODE_BURST 3
+#endif
+
+enum { MODE_NODE = 0, MODE_PRIM = 1, MODE_SHADE = 2, MODE_IDLE = 3 };
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_render_sm(const __grid_constant__ RenderArgs A)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int tile = warp % A.n_tiles;
+  const int split = warp / A.n_tiles;
+  const int x = (tile % A.tiles_x) * 8 + (lane & 7);
+  const int y = (tile / A.tiles_x) * 4 + (lane >> 3);
+  const bool valid = x < A.width && y < A.height && split < A.splits;
+  const unsigned pixel = (unsigned)(y * A.width + x);
+
+  int s = A.s_begin + split * A.chunk;
+  const int s_end = valid ? min(A.s_end, s + A.chunk) : s;
+
+  PathState st;
+  st.alive = false;
+  st.depth = 0;
+  st.tr = st.tg = st.tb = 0.0f;
+  st.o = d3_make(0, 0, 0);
+  st.d = d3_make(0, 0, 1);
+  float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+  PathCounters pc = { 0u, 0u };
+  TraceStats ts = { 0u, 0u };
+  unsigned paths = 0;
+
+  HitRec best;
+  best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
+  RayF rf;
+  int stack_ref[RTB_STACK_SIZE];
+  float stack_t[RTB_STACK_SIZE];
+  int sp = 0;
+  int cur = 0, prim_i = 0, prim_end = 0;
+  bool big_phase = false;
+  int mode = (s < s_end) ? MODE_SHADE : MODE_IDLE;
+
+  auto set_cur = [&](int ref) {
+    if (ref == RTB_REF_NONE)
+      mode = MODE_SHADE;
+    else if (ref >= 0)
+    {
+      cur = ref;
+      mode = MODE_NODE;
+    }
+    else
+    {
+      int code = ~ref;
+      prim_i = code >> 3;
+      prim_end = prim_i + (code & 7) + 1;
+      mode = MODE_PRIM;
+    }
+  };
+  auto begin_walk = [&]() {
+    big_phase = false;
+    if (!rayf_walk_setup(A.sv, st.o, st.d, best, rf))
+    {
+      mode = MODE_SHADE;
+      return;
+    }
+    sp = 0;
+    set_cur(A.sv.root_ref);
+  };
+  auto begin_ray = [&]() {
+    best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
+    rayf_basic(st.o, st.d, rf);
+    pc.rays++;
+    pc.rays_hit++;
+    if (A.sv.n_big > 0)
+    {
+      big_phase = true;
+      prim_i = 0;
+      prim_end = A.sv.n_big;
+      mode = MODE_PRIM;
+    }
+    else
+      begin_walk();
+  };
+
+  while (true)
+  {
+    const unsigned bn = __ballot_sync(0xFFFFFFFFu, mode == MODE_NODE);
+    const unsigned bp = __ballot_sync(0xFFFFFFFFu, mode == MODE_PRIM);
+    const unsigned bs = __ballot_sync(0xFFFFFFFFu, mode == MODE_SHADE);
+    if ((bn | bp | bs) == 0u)
+      break;
+    const int cn = __popc(bn), cp = __popc(bp), cs = __popc(bs);
+    if (cn >= cp && cn >= cs)
+    {
+      if (mode == MODE_NODE)
+      {
+#pragma unroll 1
+        for (int it = 0; it < RTB_NODE_BURST && mode == MODE_NODE; it++)
+        {
+          if (STATS) ts.node_visits++;
+          int nxt = node_step(A.sv, rf, cur, stack_ref, stack_t, sp);
+          if (nxt == RTB_REF_NONE)
+            nxt = stack_pop(rf, stack_ref, stack_t, sp);
+          set_cur(nxt);
+        }
+      }
+    }
+    else if (cp >= cs)
+    {
+      if (mode == MODE_PRIM)
+      {
+        PrimView p = load_prim(big_phase ? A.sv.big : A.sv.prims, prim_i);
+        test_prim_filtered<true>(p, big_phase ? ~prim_i : prim_i, st.o, st.d, rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy,
+                           rf.dfz, rf.o_abs1, best, ts.prim_tests);
+        prim_i++;
+        if (prim_i == prim_end)
+        {
+          if (big_phase)
+            begin_walk();
+          else
+          {
+            rayf_update_tmax(rf, best);
+            set_cur(stack_pop(rf, stack_ref, stack_t, sp));
+          }
+        }
+      }
+    }
+    else
+    {
+      if (mode == MODE_SHADE)
+      {
+        if (st.alive)
+        {
+          path_shade(A, st, best, pixel, (unsigned)s, sr, sg, sb, pc, nullptr);
+          if (!st.alive)
+            s++;
+        }
+        if (!st.alive && s < s_end)
+        {
+          path_begin(A, st, x, y, pixel, (unsigned)s);
+          paths++;
+        }
+        if (st.alive)
+          begin_ray();
+        else
+          mode = MODE_IDLE;
+      }
+    }
+  }
+
+  if (valid)
+  {
+    float *o = A.out + ((size_t)split * A.width * A.height + pixel) * 3;
+    o[0] = sr; o[1] = sg; o[2] = sb;
+  }
+
   unsigned long long c0 = pc.rays, c1 = pc.rays_hit, c2 = ts.prim_tests, c3 = ts.node_visits, c4 = paths;
   for (int off = 16; off > 0; off >>= 1)
   {
@@ -283,8 +476,10 @@ __global__ void k_trace_rays(const __grid_constant__ SceneView sv, const double 
   d3 d = d3_make(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
   HitRec best;
   TraceStats st = { 0u, 0u };
-  if (use_bvh)
-    closest_hit<false>(sv, o, d, best, st);
+  if (use_bvh == 2)
+    closest_hit<false, true>(sv, o, d, best, st);
+  else if (use_bvh)
+    closest_hit<false, false>(sv, o, d, best, st);
   else
     closest_hit_bruteforce(sv, o, d, best);
   bool hit = best.t < 1e300;
@@ -328,7 +523,7 @@ __global__ void k_path_records(const __grid_constant__ RenderArgs A, int sample,
   while (st.alive)
   {
     HitRec best;
-    closest_hit<false>(A.sv, st.o, st.d, best, ts);
+    closest_hit<false, false>(A.sv, st.o, st.d, best, ts);
     d3 origin = st.o;
     Surface s;
     bool hit = best.t < 1e300;
@@ -368,6 +563,11 @@ static int check_desc(const rtb_render_desc *d)
   {
     /* width/height 1 divide by zero upstream (quirk Q11) */
     rtb_set_error("rtb_render_desc: need width,height >= 2, sample_end >= sample_begin, 0 <= max_depth <= 255");
+    return RTB_EINVAL;
+  }
+  if (d->kernel < 0 || d->kernel > 3)
+  {
+    rtb_set_error("rtb_render_desc.kernel: 0 auto, 1 megakernel, 2 warp-scheduled, 3 megakernel + pre-test");
     return RTB_EINVAL;
   }
   if (d->dielectric_mode != RTB_DIELECTRIC_STOCHASTIC)
@@ -449,11 +649,11 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
       size_t need = sizeof(float) * 3 * n_px * splits;
       if (scene->scratch_bytes < need)
       {
-        RTB_CUDA(cudaStreamSynchronize(stream));
-        cudaFree(scene->d_scratch);
+        if (scene->d_scratch)
+          RTB_CUDA(cudaFreeAsync(scene->d_scratch, stream));
         scene->d_scratch = nullptr;
         scene->scratch_bytes = 0;
-        RTB_CUDA(cudaMalloc(&scene->d_scratch, need));
+        RTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scene->d_scratch), need, stream));
         scene->scratch_bytes = need;
       }
       A.out = scene->d_scratch;
@@ -463,10 +663,23 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     const int threads = 128;
     const long long warps = (long long)A.n_tiles * splits;
     const int blocks = (int)((warps * 32 + threads - 1) / threads);
-    if (counters)
-      k_render<true><<<blocks, threads, 0, stream>>>(A);
-    else
-      k_render<false><<<blocks, threads, 0, stream>>>(A);
+    /* desc->kernel: 0/1 megakernel (default), 2 warp-scheduled state machine (+FP32 sphere
+     * pre-test), 3 megakernel + FP32 sphere pre-test.  See DESIGN.md "Kernel choice". */
+    switch (desc->kernel)
+    {
+    case 2:
+      if (counters) k_render_sm<true><<<blocks, threads, 0, stream>>>(A);
+      else k_render_sm<false><<<blocks, threads, 0, stream>>>(A);
+      break;
+    case 3:
+      if (counters) k_render<true, true><<<blocks, threads, 0, stream>>>(A);
+      else k_render<false, true><<<blocks, threads, 0, stream>>>(A);
+      break;
+    default:
+      if (counters) k_render<true, false><<<blocks, threads, 0, stream>>>(A);
+      else k_render<false, false><<<blocks, threads, 0, stream>>>(A);
+      break;
+    }
     RTB_CUDA(cudaGetLastError());
     launches++;
     if (splits > 1)
@@ -529,11 +742,12 @@ extern "C" int rtb_render(rtb_scene *scene, const double *camera12, const rtb_re
   size_t n = (size_t)3 * desc->width * desc->height;
   float *d_accum = nullptr;
   uint8_t *d_fb = nullptr;
-  RTB_CUDA(cudaMalloc(&d_accum, sizeof(float) * n));
-  if (cudaMalloc(&d_fb, n) != cudaSuccess)
+  /* pooled, stream-ordered (see rtb_scene.cu: cudaMalloc/cudaFree are the dominant host cost) */
+  RTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_accum), sizeof(float) * n, 0));
+  if (cudaMallocAsync(reinterpret_cast<void **>(&d_fb), n, 0) != cudaSuccess)
   {
-    cudaFree(d_accum);
-    rtb_set_error("rtb_render: cudaMalloc framebuffer failed");
+    cudaFreeAsync(d_accum, 0);
+    rtb_set_error("rtb_render: framebuffer allocation failed");
     return RTB_ECUDA;
   }
   rc = rtb_render_accum(scene, camera12, desc, d_accum, nullptr, counters);
@@ -553,8 +767,8 @@ extern "C" int rtb_render(rtb_scene *scene, const double *camera12, const rtb_re
     if (counters)
       counters->launches += 1;
   }
-  cudaFree(d_accum);
-  cudaFree(d_fb);
+  cudaFreeAsync(d_accum, 0);
+  cudaFreeAsync(d_fb, 0);
   return rc;
 }
 

@@ -123,13 +123,6 @@ __device__ __forceinline__ unsigned float_to_ordered(float f)
   unsigned u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-static inline float ordered_to_float(unsigned u)
-{
-  unsigned v = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-  float f;
-  memcpy(&f, &v, 4);
-  return f;
-}
 
 /* bounds[0..2] = min of box_lo, bounds[3..5] = max of box_hi (ordered-uint encoded) */
 __global__ void k_bounds(const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, int n,
@@ -175,13 +168,66 @@ __device__ __forceinline__ unsigned long long spread21(unsigned v)
   return x;
 }
 
+/* Derived on the device from the scene box so the build needs no mid-way host round trip:
+ *   guard box  = scene box grown by its diagonal on every side (rays starting outside it are
+ *                re-based before the FP32 walk);
+ *   pad        = 2^-20 * (largest |coordinate| in the guard box + longest parametric distance
+ *                inside it): covers float rounding of the re-based ray and of the slab
+ *                arithmetic (DESIGN.md "Precision");
+ *   Morton grid = cubic cells over the scene box. */
+struct BuildParams
+{
+  float lo[3], hi[3];
+  float guard_lo[3], guard_hi[3];
+  float pad, inv_extent;
+  int finite;
+};
+
+__device__ __forceinline__ float ordered_to_float_dev(unsigned u)
+{
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__global__ void k_build_params(const unsigned *__restrict__ bounds, BuildParams *__restrict__ bp)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  BuildParams p;
+  bool finite = true;
+  for (int k = 0; k < 3; k++)
+  {
+    p.lo[k] = ordered_to_float_dev(bounds[k]);
+    p.hi[k] = ordered_to_float_dev(bounds[3 + k]);
+    finite = finite && isfinite(p.lo[k]) && isfinite(p.hi[k]);
+  }
+  double dx = (double)p.hi[0] - p.lo[0], dy = (double)p.hi[1] - p.lo[1], dz = (double)p.hi[2] - p.lo[2];
+  double diag = sqrt(dx * dx + dy * dy + dz * dz);
+  if (!(diag > 0.0))
+    diag = 1e-3;
+  double max_abs = 0.0;
+  for (int k = 0; k < 3; k++)
+  {
+    p.guard_lo[k] = (float)(p.lo[k] - diag);
+    p.guard_hi[k] = (float)(p.hi[k] + diag);
+    max_abs = fmax(max_abs, fmax(fabs((double)p.guard_lo[k]), fabs((double)p.guard_hi[k])));
+  }
+  p.pad = (float)((max_abs + 3.0 * diag * 1.7320508) * (1.0 / 1048576.0));
+  float ext = fmaxf(p.hi[0] - p.lo[0], fmaxf(p.hi[1] - p.lo[1], p.hi[2] - p.lo[2]));
+  p.inv_extent = ext > 0.0f ? 1.0f / ext : 0.0f;
+  p.finite = finite ? 1 : 0;
+  *bp = p;
+}
+
 __global__ void k_morton(const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, int n,
-                         float3 origin, float3 inv_extent, unsigned long long *__restrict__ keys,
+                         const BuildParams *__restrict__ bp, unsigned long long *__restrict__ keys,
                          unsigned *__restrict__ vals)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
+  const float3 origin = make_float3(bp->lo[0], bp->lo[1], bp->lo[2]);
+  const float inv = bp->inv_extent;
+  const float3 inv_extent = make_float3(inv, inv, inv);
   float4 a = box_lo[i], b = box_hi[i];
   float cx = (0.5f * (a.x + b.x) - origin.x) * inv_extent.x;
   float cy = (0.5f * (a.y + b.y) - origin.y) * inv_extent.y;
@@ -299,12 +345,13 @@ __device__ __forceinline__ int leaf_ref(int first, int count) { return ~((first 
 __global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restrict__ box_lo,
                        const float4 *__restrict__ box_hi, int n, const int2 *__restrict__ children,
                        const int *__restrict__ range_first, const float4 *__restrict__ node_lo,
-                       const float4 *__restrict__ node_hi, float pad, float4 *__restrict__ out_nodes,
-                       int *__restrict__ emitted)
+                       const float4 *__restrict__ node_hi, const BuildParams *__restrict__ bp,
+                       float4 *__restrict__ out_nodes, int *__restrict__ emitted)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1)
     return;
+  const float pad = bp->pad;
   int count = __float_as_int(node_lo[i].w);
   if (count <= RTB_LEAF_MAX)
     return;
@@ -375,14 +422,40 @@ struct HostScene
   long long n_prims = 0;
 };
 
+/* Stream-ordered, pooled device memory.  cudaMalloc/cudaFree cost 1-100+ ms each on this
+ * platform (measured: scene create 126..1145 ms for 0.6 ms of kernels), so every buffer --
+ * temporaries and the scene's own arrays -- comes from the device's default memory pool with
+ * an unlimited release threshold: after the first scene, create/destroy recycle pool memory. */
+static cudaError_t pool_setup(int device)
+{
+  static bool done[64] = { false };
+  if (device < 64 && done[device])
+    return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess)
+    return e;
+  unsigned long long threshold = ~0ull;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  if (e == cudaSuccess && device < 64)
+    done[device] = true;
+  return e;
+}
+
 template <typename T>
 struct DevBuf
 {
   T *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, 0); }
+  cudaError_t alloc(size_t n) { return cudaMallocAsync(reinterpret_cast<void **>(&p), sizeof(T) * (n ? n : 1), 0); }
   T *release() { T *q = p; p = nullptr; return q; }
 };
+
+template <typename T>
+static cudaError_t pool_alloc(T **p, size_t n)
+{
+  return cudaMallocAsync(reinterpret_cast<void **>(p), sizeof(T) * (n ? n : 1), 0);
+}
 
 void push_material(HostScene &hs, uint32_t flags, const RefVec3 &color, const RefVec3 &emission)
 {
@@ -502,6 +575,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     return RTB_EINVAL;
   }
   RTB_CUDA(cudaSetDevice(device));
+  RTB_CUDA(pool_setup(device));
 
   cudaEvent_t ev0, ev1;
   RTB_CUDA(cudaEventCreate(&ev0));
@@ -512,14 +586,11 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   std::vector<SphereIn> big_spheres, bvh_spheres;
   for (size_t i = 0; i < hs.spheres.size(); i++)
     (big[i] ? big_spheres : bvh_spheres).push_back(hs.spheres[i]);
-  /* keep the big list in loop order (cosmetic: ties are resolved by gid anyway) */
   size_t n_tris = 0;
-  bool want_tex = false;
   for (const MeshRange &m : hs.meshes)
-  {
     n_tris += m.n_tris;
-    want_tex = true; /* texcoords ride along with every mesh (24 B/triangle, only read for M_CHECKERED) */
-  }
+  /* texcoords ride along with every mesh (24 B/triangle, only read for M_CHECKERED) */
+  const bool want_tex = n_tris > 0;
   const size_t n_bs = bvh_spheres.size();
   const size_t N = n_bs + n_tris; /* primitives in the tree */
 
@@ -528,23 +599,20 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   sc->device = device;
   size_t dev_bytes = 0;
 
-  /* materials */
-  RTB_CUDA(cudaMalloc(&sc->d_mats, sizeof(float4) * std::max<size_t>(2, hs.mats.size())));
+  /* materials, counters, big list */
+  RTB_CUDA(pool_alloc(&sc->d_mats, std::max<size_t>(2, hs.mats.size())));
   if (!hs.mats.empty())
-    RTB_CUDA(cudaMemcpy(sc->d_mats, hs.mats.data(), sizeof(float4) * hs.mats.size(), cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpyAsync(sc->d_mats, hs.mats.data(), sizeof(float4) * hs.mats.size(), cudaMemcpyHostToDevice, 0));
   dev_bytes += sizeof(float4) * hs.mats.size();
-  RTB_CUDA(cudaMalloc(&sc->d_counters, sizeof(unsigned long long) * 8));
-
-  /* big list */
-  RTB_CUDA(cudaMalloc(&sc->d_big, sizeof(PrimRec) * std::max<size_t>(1, big_spheres.size())));
+  RTB_CUDA(pool_alloc(&sc->d_counters, 8));
+  RTB_CUDA(pool_alloc(&sc->d_big, 3 * std::max<size_t>(1, big_spheres.size())));
+  DevBuf<SphereIn> d_big_in, d_bvh_in;
   if (!big_spheres.empty())
   {
-    DevBuf<SphereIn> d_in;
-    RTB_CUDA(d_in.alloc(big_spheres.size()));
-    RTB_CUDA(cudaMemcpy(d_in.p, big_spheres.data(), sizeof(SphereIn) * big_spheres.size(), cudaMemcpyHostToDevice));
-    k_marshal_spheres<<<1, 32>>>(d_in.p, (int)big_spheres.size(), reinterpret_cast<PrimRec *>(sc->d_big), nullptr, nullptr);
+    RTB_CUDA(d_big_in.alloc(big_spheres.size()));
+    RTB_CUDA(cudaMemcpyAsync(d_big_in.p, big_spheres.data(), sizeof(SphereIn) * big_spheres.size(), cudaMemcpyHostToDevice, 0));
+    k_marshal_spheres<<<1, 32>>>(d_big_in.p, (int)big_spheres.size(), reinterpret_cast<PrimRec *>(sc->d_big), nullptr, nullptr);
     RTB_CUDA(cudaGetLastError());
-    RTB_CUDA(cudaDeviceSynchronize());
   }
   dev_bytes += sizeof(PrimRec) * big_spheres.size();
 
@@ -554,39 +622,53 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   view.n_prims = (int)N;
   view.root_ref = RTB_REF_NONE;
   view.tex = nullptr;
+  for (int k = 0; k < 3; k++)
+  {
+    view.guard_lo[k] = -FLT_MAX;
+    view.guard_hi[k] = FLT_MAX;
+  }
   int bvh_depth = 0;
   size_t n_nodes = 0;
+
+  /* every temporary lives until the end of this function; frees are stream-ordered */
+  DevBuf<PrimRec> d_unsorted;
+  DevBuf<float4> d_lo, d_hi, d_node_lo, d_node_hi;
+  DevBuf<float2> d_tex_unsorted;
+  DevBuf<RefVertex> d_stage;
+  DevBuf<unsigned> d_bounds, d_vals, d_vals_sorted;
+  DevBuf<BuildParams> d_bp;
+  DevBuf<unsigned long long> d_keys, d_keys_sorted;
+  DevBuf<unsigned char> d_temp;
+  DevBuf<int2> d_children;
+  DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc;
+  BuildParams h_bp;
+  memset(&h_bp, 0, sizeof(h_bp));
+  int h_misc[2] = { 0, 0 };
 
   if (N > 0)
   {
     const int T = 256;
     const int blocks = (int)((N + T - 1) / T);
-    DevBuf<PrimRec> d_unsorted;
-    DevBuf<float4> d_lo, d_hi;
-    DevBuf<float2> d_tex_unsorted;
     RTB_CUDA(d_unsorted.alloc(N));
     RTB_CUDA(d_lo.alloc(N));
     RTB_CUDA(d_hi.alloc(N));
     if (want_tex)
     {
       RTB_CUDA(d_tex_unsorted.alloc(3 * N));
-      RTB_CUDA(cudaMemset(d_tex_unsorted.p, 0, sizeof(float2) * 3 * N));
+      if (n_bs)
+        RTB_CUDA(cudaMemsetAsync(d_tex_unsorted.p, 0, sizeof(float2) * 3 * n_bs, 0));
     }
-
     if (n_bs)
     {
-      DevBuf<SphereIn> d_in;
-      RTB_CUDA(d_in.alloc(n_bs));
-      RTB_CUDA(cudaMemcpy(d_in.p, bvh_spheres.data(), sizeof(SphereIn) * n_bs, cudaMemcpyHostToDevice));
-      k_marshal_spheres<<<(int)((n_bs + T - 1) / T), T>>>(d_in.p, (int)n_bs, d_unsorted.p, d_lo.p, d_hi.p);
+      RTB_CUDA(d_bvh_in.alloc(n_bs));
+      RTB_CUDA(cudaMemcpyAsync(d_bvh_in.p, bvh_spheres.data(), sizeof(SphereIn) * n_bs, cudaMemcpyHostToDevice, 0));
+      k_marshal_spheres<<<(int)((n_bs + T - 1) / T), T>>>(d_bvh_in.p, (int)n_bs, d_unsorted.p, d_lo.p, d_hi.p);
       RTB_CUDA(cudaGetLastError());
-      RTB_CUDA(cudaDeviceSynchronize());
     }
     {
       /* raw Vertex arrays go up as they are (120 B per triangle) and are converted on the
        * device; staging is bounded so huge meshes do not double their footprint */
-      const size_t chunk_tris = 1u << 20;
-      DevBuf<RefVertex> d_stage;
+      const size_t chunk_tris = 1u << 21;
       size_t max_chunk = 0;
       for (const MeshRange &m : hs.meshes)
         max_chunk = std::max(max_chunk, std::min(chunk_tris, m.n_tris));
@@ -598,92 +680,55 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
         for (size_t t0 = 0; t0 < m.n_tris; t0 += chunk_tris)
         {
           size_t cnt = std::min(chunk_tris, m.n_tris - t0);
-          RTB_CUDA(cudaMemcpy(d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, cudaMemcpyHostToDevice));
+          RTB_CUDA(cudaMemcpyAsync(d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, cudaMemcpyHostToDevice, 0));
           k_marshal_tris<<<(int)((cnt + T - 1) / T), T>>>(d_stage.p, (int)cnt, m.obj, (int)(m.gid_first + (long long)t0),
                                                           d_unsorted.p + offset, d_lo.p + offset, d_hi.p + offset,
                                                           want_tex ? d_tex_unsorted.p + 3 * offset : nullptr);
           RTB_CUDA(cudaGetLastError());
-          RTB_CUDA(cudaDeviceSynchronize());
           offset += cnt;
         }
       }
     }
 
-    /* scene box of the tree primitives */
-    DevBuf<unsigned> d_bounds;
+    /* scene box -> guard box, padding, Morton grid (all on the device) */
     RTB_CUDA(d_bounds.alloc(6));
-    unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
-    RTB_CUDA(cudaMemcpy(d_bounds.p, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice));
+    RTB_CUDA(d_bp.alloc(1));
+    static const unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+    RTB_CUDA(cudaMemcpyAsync(d_bounds.p, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, 0));
     k_bounds<<<std::min(blocks, 1184), T>>>(d_lo.p, d_hi.p, (int)N, d_bounds.p);
     RTB_CUDA(cudaGetLastError());
-    unsigned hb[6];
-    RTB_CUDA(cudaMemcpy(hb, d_bounds.p, sizeof(hb), cudaMemcpyDeviceToHost));
-    float lo[3], hi[3];
-    for (int k = 0; k < 3; k++)
-    {
-      lo[k] = ordered_to_float(hb[k]);
-      hi[k] = ordered_to_float(hb[3 + k]);
-    }
-    for (int k = 0; k < 3; k++)
-      if (!std::isfinite(lo[k]) || !std::isfinite(hi[k]))
-      {
-        rtb_set_error("non-finite geometry");
-        return RTB_EINVAL;
-      }
-    double diag = std::sqrt((double)(hi[0] - lo[0]) * (hi[0] - lo[0]) + (double)(hi[1] - lo[1]) * (hi[1] - lo[1]) +
-                            (double)(hi[2] - lo[2]) * (hi[2] - lo[2]));
-    if (diag <= 0) diag = 1e-3;
-    double max_abs = 0;
-    for (int k = 0; k < 3; k++)
-    {
-      view.guard_lo[k] = (float)(lo[k] - diag);
-      view.guard_hi[k] = (float)(hi[k] + diag);
-      max_abs = std::max(max_abs, std::max(std::fabs((double)view.guard_lo[k]), std::fabs((double)view.guard_hi[k])));
-    }
-    /* padding that covers float rounding of the (re-based) ray and of the slab arithmetic:
-     * 2^-20 * (largest origin coordinate + longest parametric distance inside the guard box) */
-    float pad = (float)((max_abs + 3.0 * diag * 1.7320508) * (1.0 / 1048576.0));
+    k_build_params<<<1, 32>>>(d_bounds.p, d_bp.p);
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaMemcpyAsync(&h_bp, d_bp.p, sizeof(h_bp), cudaMemcpyDeviceToHost, 0));
+
+    RTB_CUDA(pool_alloc(&sc->d_prims, 3 * N));
+    if (want_tex)
+      RTB_CUDA(pool_alloc(&sc->d_tex, 3 * N));
 
     if (N <= RTB_LEAF_MAX)
     {
       /* a single leaf; order = insertion order */
-      RTB_CUDA(cudaMalloc(&sc->d_prims, sizeof(PrimRec) * N));
-      RTB_CUDA(cudaMemcpy(sc->d_prims, d_unsorted.p, sizeof(PrimRec) * N, cudaMemcpyDeviceToDevice));
+      RTB_CUDA(cudaMemcpyAsync(sc->d_prims, d_unsorted.p, sizeof(PrimRec) * N, cudaMemcpyDeviceToDevice, 0));
       if (want_tex)
-      {
-        RTB_CUDA(cudaMalloc(&sc->d_tex, sizeof(float2) * 3 * N));
-        RTB_CUDA(cudaMemcpy(sc->d_tex, d_tex_unsorted.p, sizeof(float2) * 3 * N, cudaMemcpyDeviceToDevice));
-      }
-      RTB_CUDA(cudaMalloc(&sc->d_nodes, sizeof(BvhNode)));
+        RTB_CUDA(cudaMemcpyAsync(sc->d_tex, d_tex_unsorted.p, sizeof(float2) * 3 * N, cudaMemcpyDeviceToDevice, 0));
+      RTB_CUDA(pool_alloc(&sc->d_nodes, 4));
       view.root_ref = ~(((0) << 3) | ((int)N - 1));
-      bvh_depth = 0;
     }
     else
     {
-      DevBuf<unsigned long long> d_keys, d_keys_sorted;
-      DevBuf<unsigned> d_vals, d_vals_sorted;
       RTB_CUDA(d_keys.alloc(N));
       RTB_CUDA(d_keys_sorted.alloc(N));
       RTB_CUDA(d_vals.alloc(N));
       RTB_CUDA(d_vals_sorted.alloc(N));
-      float3 origin = make_float3(lo[0], lo[1], lo[2]);
-      /* cubic Morton cells: one scale for all axes (flat scenes keep their resolution) */
-      float max_extent = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
-      float inv = max_extent > 0.0f ? 1.0f / max_extent : 0.0f;
-      float3 inv_extent = make_float3(inv, inv, inv);
-      k_morton<<<blocks, T>>>(d_lo.p, d_hi.p, (int)N, origin, inv_extent, d_keys.p, d_vals.p);
+      k_morton<<<blocks, T>>>(d_lo.p, d_hi.p, (int)N, d_bp.p, d_keys.p, d_vals.p);
       RTB_CUDA(cudaGetLastError());
       size_t temp_bytes = 0;
       RTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p,
-                                               d_vals_sorted.p, (int)N, 0, 63));
-      DevBuf<unsigned char> d_temp;
+                                               d_vals_sorted.p, (int)N, 0, 63, 0));
       RTB_CUDA(d_temp.alloc(temp_bytes));
       RTB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys.p, d_keys_sorted.p, d_vals.p,
-                                               d_vals_sorted.p, (int)N, 0, 63));
+                                               d_vals_sorted.p, (int)N, 0, 63, 0));
 
-      DevBuf<int2> d_children;
-      DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc;
-      DevBuf<float4> d_node_lo, d_node_hi;
       RTB_CUDA(d_children.alloc(N - 1));
       RTB_CUDA(d_parent_inner.alloc(N - 1));
       RTB_CUDA(d_parent_leaf.alloc(N));
@@ -692,8 +737,8 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       RTB_CUDA(d_misc.alloc(2));
       RTB_CUDA(d_node_lo.alloc(N - 1));
       RTB_CUDA(d_node_hi.alloc(N - 1));
-      RTB_CUDA(cudaMemset(d_flags.p, 0, sizeof(int) * (N - 1)));
-      RTB_CUDA(cudaMemset(d_misc.p, 0, sizeof(int) * 2));
+      RTB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * (N - 1), 0));
+      RTB_CUDA(cudaMemsetAsync(d_misc.p, 0, sizeof(int) * 2, 0));
       k_karras<<<blocks, T>>>(d_keys_sorted.p, (int)N, d_children.p, d_parent_inner.p, d_parent_leaf.p, d_first.p);
       RTB_CUDA(cudaGetLastError());
       k_fit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_parent_inner.p,
@@ -702,26 +747,15 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       k_depth<<<blocks, T>>>((int)N, d_parent_inner.p, d_parent_leaf.p, d_misc.p);
       RTB_CUDA(cudaGetLastError());
 
-      RTB_CUDA(cudaMalloc(&sc->d_nodes, sizeof(BvhNode) * (N - 1)));
-      RTB_CUDA(cudaMemset(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1)));
+      RTB_CUDA(pool_alloc(&sc->d_nodes, 4 * (N - 1)));
+      RTB_CUDA(cudaMemsetAsync(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1), 0));
       k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
-                            d_node_hi.p, pad, sc->d_nodes, d_misc.p + 1);
+                            d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1);
       RTB_CUDA(cudaGetLastError());
-      RTB_CUDA(cudaMalloc(&sc->d_prims, sizeof(PrimRec) * N));
-      if (want_tex)
-        RTB_CUDA(cudaMalloc(&sc->d_tex, sizeof(float2) * 3 * N));
       k_reorder<<<blocks, T>>>(d_vals_sorted.p, (int)N, d_unsorted.p, reinterpret_cast<PrimRec *>(sc->d_prims),
                                want_tex ? d_tex_unsorted.p : nullptr, sc->d_tex);
       RTB_CUDA(cudaGetLastError());
-      int misc[2];
-      RTB_CUDA(cudaMemcpy(misc, d_misc.p, sizeof(misc), cudaMemcpyDeviceToHost));
-      bvh_depth = misc[0];
-      n_nodes = (size_t)misc[1];
-      if (bvh_depth > RTB_STACK_SIZE - 2)
-      {
-        rtb_set_error("BVH deeper than the traversal stack");
-        return RTB_EINVAL;
-      }
+      RTB_CUDA(cudaMemcpyAsync(h_misc, d_misc.p, sizeof(h_misc), cudaMemcpyDeviceToHost, 0));
       view.root_ref = 0;
       dev_bytes += sizeof(BvhNode) * (N - 1);
     }
@@ -729,21 +763,36 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   }
   else
   {
-    RTB_CUDA(cudaMalloc(&sc->d_prims, sizeof(PrimRec)));
-    RTB_CUDA(cudaMalloc(&sc->d_nodes, sizeof(BvhNode)));
-    for (int k = 0; k < 3; k++)
-    {
-      view.guard_lo[k] = -FLT_MAX;
-      view.guard_hi[k] = FLT_MAX;
-    }
+    RTB_CUDA(pool_alloc(&sc->d_prims, 3));
+    RTB_CUDA(pool_alloc(&sc->d_nodes, 4));
   }
-  RTB_CUDA(cudaDeviceSynchronize());
   RTB_CUDA(cudaEventRecord(ev1, 0));
-  RTB_CUDA(cudaEventSynchronize(ev1));
+  RTB_CUDA(cudaEventSynchronize(ev1)); /* the only host wait of the build */
   float ms = 0;
   RTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+
+  if (N > 0)
+  {
+    if (!h_bp.finite)
+    {
+      rtb_set_error("non-finite geometry");
+      return RTB_EINVAL;
+    }
+    for (int k = 0; k < 3; k++)
+    {
+      view.guard_lo[k] = h_bp.guard_lo[k];
+      view.guard_hi[k] = h_bp.guard_hi[k];
+    }
+    bvh_depth = h_misc[0];
+    n_nodes = (size_t)h_misc[1];
+    if (bvh_depth > RTB_STACK_SIZE - 2)
+    {
+      rtb_set_error("BVH deeper than the traversal stack");
+      return RTB_EINVAL;
+    }
+  }
 
   view.nodes = sc->d_nodes;
   view.prims = sc->d_prims;
@@ -822,12 +871,12 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
   if (!scene)
     return;
   cudaSetDevice(scene->device);
-  cudaFree(scene->d_nodes);
-  cudaFree(scene->d_prims);
-  cudaFree(scene->d_big);
-  cudaFree(scene->d_mats);
-  cudaFree(scene->d_tex);
-  cudaFree(scene->d_scratch);
-  cudaFree(scene->d_counters);
+  /* stream-ordered: the memory goes back to the pool once work queued before this point on
+   * the legacy default stream (which synchronises with every blocking stream) is done */
+  void *bufs[] = { scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_tex,
+                   scene->d_scratch, scene->d_counters };
+  for (void *b : bufs)
+    if (b)
+      cudaFreeAsync(b, 0);
   delete scene;
 }
