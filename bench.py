@@ -233,14 +233,14 @@ def main_gpu(args):
     fb_host = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
-    desc = api.make_desc(W, H, rank * spp, (rank + 1) * spp, max_depth=depth, seed=SEED)
+    s_begin, s_end, total_spp = pkg.sharding.shard_weak(rank, world, spp)
+    desc = api.make_desc(W, H, s_begin, s_end, max_depth=depth, seed=SEED)
 
     def step():
         scene.render_accum(cam, desc, accum.data_ptr(), stream=stream.cuda_stream)
-        if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        pkg.sharding.reduce_to_root(accum, world)
         if rank == 0:
-            api.tonemap(accum.data_ptr(), W, H, world * spp, fb.data_ptr(), device=local, stream=stream.cuda_stream)
+            api.tonemap(accum.data_ptr(), W, H, total_spp, fb.data_ptr(), device=local, stream=stream.cuda_stream)
 
     def sync_all():
         if world > 1:
