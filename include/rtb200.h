@@ -62,8 +62,9 @@ typedef struct
   int max_depth;                /* run-time MAX_DEPTH (raytracer.h:25); path dies at depth > max_depth */
   int dielectric_mode;          /* RTB_DIELECTRIC_* */
   uint64_t seed;                /* Philox key */
-  int kernel;                   /* 0 = auto, 1 = megakernel, 2 = warp-scheduled state machine, 3 = megakernel + FP32 pre-test */
-  int reserved;
+  int kernel;                   /* 0 = auto; 1 megakernel (if-if walk); 2 warp-scheduled state machine;
+                                   3 megakernel + FP32 sphere pre-test; 4 while-while walk; 5 suspendable walk */
+  int reserved;                 /* kernel 5 tuning: suspend threshold in lanes (0 = default) */
 } rtb_render_desc;
 
 typedef struct

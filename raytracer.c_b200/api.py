@@ -14,7 +14,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_CUDA = os.path.join(_HERE, "librtb200.so")
+LIB_CUDA = os.environ.get("RTB200_LIB_OVERRIDE") or os.path.join(_HERE, "librtb200.so")  # override: dev A/B builds only
 LIB_HOST = os.path.join(_HERE, "libraytracer_b200.so")
 
 # every symbol include/rtb200.h declares
@@ -220,7 +220,7 @@ def render(objects, camera, width, height, samples):
 
 # ---- the C ABI ----------------------------------------------------------------------------
 
-def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0):
+def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0):
     d = abi.RtbRenderDesc()
     d.width, d.height = width, height
     d.sample_begin, d.sample_end = sample_begin, sample_end
@@ -228,6 +228,7 @@ def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCE
     d.dielectric_mode = 0
     d.seed = seed
     d.kernel = kernel
+    d.reserved = tune
     return d
 
 

@@ -198,8 +198,10 @@ __device__ __forceinline__ void test_prim(const PrimView &p, int slot, const d3 
  * Error model: every coordinate entering the test is rounded to float (relative 2^-24);
  * A = |c|_1 + r + |o|_1 bounds every intermediate magnitude, linear quantities (L, tca) are
  * off by at most e = A*2^-20, quadratic ones (d2, r2-d2) by at most eq = 10*A*A*2^-20. */
-__device__ __forceinline__ bool sphere_may_win(const PrimView &p, float ofx, float ofy, float ofz, float dfx,
-                                               float dfy, float dfz, float o_abs1, float best_t_up)
+/* returns false if the reference's test certainly misses; otherwise t_lo = a lower bound of
+ * the t it would report */
+__device__ __forceinline__ bool sphere_lower_bound(const PrimView &p, float ofx, float ofy, float ofz, float dfx,
+                                                   float dfy, float dfz, float o_abs1, float &t_lo)
 {
   float cx = (float)p.cx(), cy = (float)p.cy(), cz = (float)p.cz(), r = (float)p.radius();
   float A = (fabsf(cx) + fabsf(cy) + fabsf(cz) + fabsf(r) + o_abs1) * 1.0000005f;
@@ -214,7 +216,16 @@ __device__ __forceinline__ bool sphere_may_win(const PrimView &p, float ofx, flo
   if (disc < -eq)
     return false;
   float thc_hi = sqrtf(fmaxf(disc + eq, 0.0f)) * 1.000001f;
-  float t_lo = tca - e - thc_hi;                 /* lower bound of the near root */
+  t_lo = tca - e - thc_hi;                       /* lower bound of the near root */
+  return true;
+}
+
+__device__ __forceinline__ bool sphere_may_win(const PrimView &p, float ofx, float ofy, float ofz, float dfx,
+                                               float dfy, float dfz, float o_abs1, float best_t_up)
+{
+  float t_lo;
+  if (!sphere_lower_bound(p, ofx, ofy, ofz, dfx, dfy, dfz, o_abs1, t_lo))
+    return false;
   return !(t_lo > best_t_up);
 }
 
@@ -251,7 +262,7 @@ struct RayF
   float oodx, oody, oodz; /* (re-based origin) * idir */
   float o_abs1;           /* |o|_1 of the original origin */
   float tmax;             /* walk bound in the re-based frame */
-  double t_base;          /* parametric offset of the re-based origin */
+  float t_base;           /* parametric offset of the re-based origin */
 };
 
 #define RTB_WIDEN 1.0000005f /* > (1+2^-23)^4: slab arithmetic rounding */
@@ -278,7 +289,7 @@ __device__ __forceinline__ bool rayf_walk_setup(const SceneView &sv, const d3 &o
   if (fabsf(dfy) < tiny) dfy = copysignf(tiny, dfy);
   if (fabsf(dfz) < tiny) dfz = copysignf(tiny, dfz);
   rf.idx = 1.0f / dfx; rf.idy = 1.0f / dfy; rf.idz = 1.0f / dfz;
-  rf.t_base = 0.0;
+  rf.t_base = 0.0f;
   bool outside = ofx < sv.guard_lo[0] || ofx > sv.guard_hi[0] || ofy < sv.guard_lo[1] ||
                  ofy > sv.guard_hi[1] || ofz < sv.guard_lo[2] || ofz > sv.guard_hi[2];
   if (outside)
@@ -294,21 +305,21 @@ __device__ __forceinline__ bool rayf_walk_setup(const SceneView &sv, const d3 &o
       return false;
     if (t_in > 0.0f)
     {
-      rf.t_base = (double)(t_in * 0.999f);
-      ofx = (float)fma(d.x, rf.t_base, o.x);
-      ofy = (float)fma(d.y, rf.t_base, o.y);
-      ofz = (float)fma(d.z, rf.t_base, o.z);
+      rf.t_base = t_in * 0.999f;
+      ofx = (float)fma(d.x, (double)rf.t_base, o.x);
+      ofy = (float)fma(d.y, (double)rf.t_base, o.y);
+      ofz = (float)fma(d.z, (double)rf.t_base, o.z);
     }
   }
   rf.oodx = ofx * rf.idx; rf.oody = ofy * rf.idy; rf.oodz = ofz * rf.idz;
-  rf.tmax = (best.t >= 1e30) ? 3.0e38f : __double2float_ru(best.t - rf.t_base) * RTB_WIDEN;
+  rf.tmax = (best.t >= 1e30) ? 3.0e38f : __double2float_ru(best.t - (double)rf.t_base) * RTB_WIDEN;
   return true;
 }
 
 __device__ __forceinline__ void rayf_update_tmax(RayF &rf, const HitRec &best)
 {
   if (best.t < 1e30)
-    rf.tmax = __double2float_ru(best.t - rf.t_base) * RTB_WIDEN;
+    rf.tmax = __double2float_ru(best.t - (double)rf.t_base) * RTB_WIDEN;
 }
 
 /* One inner node: tests both children, returns the reference to continue with
@@ -400,6 +411,92 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
                              rf.dfy, rf.dfz, rf.o_abs1, best, exact);
         rayf_update_tmax(rf, best);
       }
+      cur = stack_pop(rf, stack_ref, stack_t, sp);
+    }
+  }
+  if (STATS) st.prim_tests += exact;
+}
+
+/* oversized list, "select, then test": an FP32 lower bound per sphere picks the most
+ * promising one, which all lanes test exactly at once; the few others whose bound still
+ * beats the result follow */
+__device__ __forceinline__ void big_list_select_test(const SceneView &sv, const d3 &o, const d3 &d, const RayF &rf,
+                                                     HitRec &best, unsigned &exact)
+{
+  if (sv.n_big <= 0)
+    return;
+  float tlo_min = 3.0e38f;
+  int kmin = -1;
+  unsigned mask = 0u;
+  for (int k = 0; k < sv.n_big; k++)
+  {
+    float tlo;
+    if (sphere_lower_bound(load_prim(sv.big, k), rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy, rf.dfz, rf.o_abs1, tlo))
+    {
+      mask |= 1u << k;
+      if (tlo < tlo_min)
+      {
+        tlo_min = tlo;
+        kmin = k;
+      }
+    }
+  }
+  if (kmin >= 0)
+  {
+    test_prim(load_prim(sv.big, kmin), ~kmin, o, d, best);
+    exact++;
+    mask &= ~(1u << kmin);
+  }
+  while (mask)
+  {
+    int k = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    test_prim_filtered<true>(load_prim(sv.big, k), ~k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy, rf.dfz,
+                             rf.o_abs1, best, exact);
+  }
+}
+
+/* "while-while" variant (Aila & Laine 2009): all lanes first walk inner nodes until each has
+ * reached a leaf, then the leaf tests run together.  The exact FP64 tests -- the expensive
+ * part -- are executed with most lanes active instead of one or two
+ * (profiles/r1_c3_megakernel_ncu.md).  The oversized list is handled "select, then test":
+ * an FP32 lower bound per sphere picks the most promising one, which is tested exactly by
+ * all lanes at once; the few others whose bound still beats the result follow. */
+template <bool STATS>
+__device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best,
+                                               TraceStats &st)
+{
+  best.t = DBL_MAX;
+  best.gid = 0x7FFFFFFF;
+  best.slot = 0;
+  RayF rf;
+  rayf_basic(o, d, rf);
+  unsigned exact = 0;
+
+  big_list_select_test(sv, o, d, rf, best, exact);
+
+  if (rayf_walk_setup(sv, o, d, best, rf))
+  {
+    int stack_ref[RTB_STACK_SIZE];
+    float stack_t[RTB_STACK_SIZE];
+    int sp = 0;
+    int cur = sv.root_ref;
+    while (cur != RTB_REF_NONE)
+    {
+      while (cur >= 0 && cur != RTB_REF_NONE)
+      {
+        if (STATS) st.node_visits++;
+        int nxt = node_step(sv, rf, cur, stack_ref, stack_t, sp);
+        cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack_ref, stack_t, sp);
+      }
+      if (cur == RTB_REF_NONE)
+        break;
+      int code = ~cur;
+      int first = code >> 3, count = (code & 7) + 1;
+      for (int k = 0; k < count; k++)
+        test_prim_filtered<false>(load_prim(sv.prims, first + k), first + k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx,
+                                  rf.dfy, rf.dfz, rf.o_abs1, best, exact);
+      rayf_update_tmax(rf, best);
       cur = stack_pop(rf, stack_ref, stack_t, sp);
     }
   }

@@ -26,6 +26,7 @@ struct RenderArgs
   int width, height, tiles_x, n_tiles;
   int s_begin, s_end, chunk, splits;
   int max_depth, dielectric_mode;
+  int suspend_lanes; /* k_render_pw: suspend the walk when fewer lanes than this are walking */
   uint2 key;
   float *out; /* [splits][height*width*3] */
   unsigned long long *counters;
@@ -165,8 +166,9 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
   }
 }
 
-template <bool STATS, bool FILTER>
-__global__ void __launch_bounds__(128) k_render(const __grid_constant__ RenderArgs A)
+/* WALK: 0 = if-if loop, 1 = if-if + FP32 sphere pre-test, 2 = while-while + select-then-test */
+template <bool STATS, int WALK>
+__global__ void __launch_bounds__(128, WALK == 2 ? 8 : 4) k_render(const __grid_constant__ RenderArgs A)
 {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -205,7 +207,10 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ RenderAr
       HitRec best;
       pc.rays++;
       pc.rays_hit++;
-      closest_hit<STATS, FILTER>(A.sv, st.o, st.d, best, ts);
+      if (WALK == 2)
+        closest_hit_ww<STATS>(A.sv, st.o, st.d, best, ts);
+      else
+        closest_hit<STATS, WALK == 1>(A.sv, st.o, st.d, best, ts);
       path_shade(A, st, best, pixel, (unsigned)s, sr, sg, sb, pc, nullptr);
       if (!st.alive)
         s++;
@@ -437,6 +442,153 @@ __global__ void __launch_bounds__(128) k_render_sm(const __grid_constant__ Rende
   }
 }
 
+/* ---- megakernel with a SUSPENDABLE walk -------------------------------------------------------
+ * profiles/r1_c3_k4_ncu.md: with the while-while walk only ~4 of 32 lanes are walking on
+ * average -- traversal lengths have a long tail and a warp waits for its slowest ray at every
+ * bounce.  Here a lane's walk state (current node, stack, best hit) survives across loop
+ * trips: as soon as fewer than RTB_SUSPEND_LANES lanes are still walking AND some lanes are
+ * waiting with a finished query, the walkers are suspended, the waiting lanes are shaded and
+ * given their next ray (next bounce, or the pixel's next sample), and everybody resumes
+ * walking together.  This is the persistent-threads "replace finished rays" idea (Aila &
+ * Laine) inside the megakernel: no ray queues in memory, state stays in registers. */
+#ifndef RTB_SUSPEND_LANES
+#define RTB_SUSPEND_LANES 20
+#endif
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ RenderArgs A)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int tile = warp % A.n_tiles;
+  const int split = warp / A.n_tiles;
+  const int x = (tile % A.tiles_x) * 8 + (lane & 7);
+  const int y = (tile / A.tiles_x) * 4 + (lane >> 3);
+  const bool valid = x < A.width && y < A.height && split < A.splits;
+  const unsigned pixel = (unsigned)(y * A.width + x);
+
+  int s = A.s_begin + split * A.chunk;
+  const int s_end = valid ? min(A.s_end, s + A.chunk) : s;
+
+  PathState st;
+  st.alive = false;
+  st.depth = 0;
+  st.tr = st.tg = st.tb = 0.0f;
+  st.o = d3_make(0, 0, 0);
+  st.d = d3_make(0, 0, 1);
+  float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+  PathCounters pc = { 0u, 0u };
+  TraceStats ts = { 0u, 0u };
+  unsigned paths = 0;
+
+  HitRec best;
+  best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
+  RayF rf;
+  rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
+  int stack_ref[RTB_STACK_SIZE];
+  float stack_t[RTB_STACK_SIZE];
+  int sp = 0;
+  int cur = RTB_REF_NONE;
+  bool walking = false;
+
+  while (true)
+  {
+    if (!walking)
+    {
+      if (st.alive)
+      {
+        path_shade(A, st, best, pixel, (unsigned)s, sr, sg, sb, pc, nullptr);
+        if (!st.alive)
+          s++;
+      }
+      if (!st.alive && s < s_end)
+      {
+        path_begin(A, st, x, y, pixel, (unsigned)s);
+        paths++;
+      }
+      if (st.alive)
+      {
+        pc.rays++;
+        pc.rays_hit++;
+        best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
+        rayf_basic(st.o, st.d, rf);
+        big_list_select_test(A.sv, st.o, st.d, rf, best, ts.prim_tests);
+        if (rayf_walk_setup(A.sv, st.o, st.d, best, rf))
+        {
+          sp = 0;
+          cur = A.sv.root_ref;
+          walking = cur != RTB_REF_NONE;
+        }
+      }
+    }
+    if (__all_sync(0xFFFFFFFFu, !st.alive))
+      break;
+
+    while (true)
+    {
+      const unsigned bw = __ballot_sync(0xFFFFFFFFu, walking);
+      if (bw == 0u)
+        break;
+      const unsigned bwait = __ballot_sync(0xFFFFFFFFu, st.alive && !walking);
+      if (bwait != 0u && __popc(bw) < A.suspend_lanes)
+        break;
+      if (walking)
+      {
+        while (cur >= 0 && cur != RTB_REF_NONE)
+        {
+          if (STATS) ts.node_visits++;
+          int nxt = node_step(A.sv, rf, cur, stack_ref, stack_t, sp);
+          cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack_ref, stack_t, sp);
+        }
+        if (cur != RTB_REF_NONE)
+        {
+          int code = ~cur;
+          int first = code >> 3, count = (code & 7) + 1;
+          for (int k = 0; k < count; k++)
+          {
+            test_prim(load_prim(A.sv.prims, first + k), first + k, st.o, st.d, best);
+            if (STATS) ts.prim_tests++;
+          }
+          rayf_update_tmax(rf, best);
+          cur = stack_pop(rf, stack_ref, stack_t, sp);
+        }
+        if (cur == RTB_REF_NONE)
+          walking = false;
+      }
+    }
+  }
+
+  if (valid)
+  {
+    float *o = A.out + ((size_t)split * A.width * A.height + pixel) * 3;
+    o[0] = sr; o[1] = sg; o[2] = sb;
+  }
+
+  unsigned long long c0 = pc.rays, c1 = pc.rays_hit, c2 = ts.prim_tests, c3 = ts.node_visits, c4 = paths;
+  for (int off = 16; off > 0; off >>= 1)
+  {
+    c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, off);
+    c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, off);
+    c4 += __shfl_xor_sync(0xFFFFFFFFu, c4, off);
+    if (STATS)
+    {
+      c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, off);
+      c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, off);
+    }
+  }
+  if (lane == 0)
+  {
+    atomicAdd(&A.counters[0], c0);
+    atomicAdd(&A.counters[1], c1);
+    atomicAdd(&A.counters[4], c4);
+    if (STATS)
+    {
+      atomicAdd(&A.counters[2], c2);
+      atomicAdd(&A.counters[3], c3);
+    }
+  }
+}
+
 /* sum of the split planes, in plane order (deterministic) */
 __global__ void k_sum_planes(const float *__restrict__ planes, int splits, size_t n, float *__restrict__ out)
 {
@@ -476,7 +628,9 @@ __global__ void k_trace_rays(const __grid_constant__ SceneView sv, const double 
   d3 d = d3_make(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
   HitRec best;
   TraceStats st = { 0u, 0u };
-  if (use_bvh == 2)
+  if (use_bvh == 3)
+    closest_hit_ww<false>(sv, o, d, best, st);
+  else if (use_bvh == 2)
     closest_hit<false, true>(sv, o, d, best, st);
   else if (use_bvh)
     closest_hit<false, false>(sv, o, d, best, st);
@@ -565,7 +719,7 @@ static int check_desc(const rtb_render_desc *d)
     rtb_set_error("rtb_render_desc: need width,height >= 2, sample_end >= sample_begin, 0 <= max_depth <= 255");
     return RTB_EINVAL;
   }
-  if (d->kernel < 0 || d->kernel > 3)
+  if (d->kernel < 0 || d->kernel > 5)
   {
     rtb_set_error("rtb_render_desc.kernel: 0 auto, 1 megakernel, 2 warp-scheduled, 3 megakernel + pre-test");
     return RTB_EINVAL;
@@ -596,6 +750,7 @@ static void fill_args(RenderArgs &A, const rtb_scene *scene, const double *camer
   A.s_end = desc->sample_end;
   A.max_depth = desc->max_depth;
   A.dielectric_mode = desc->dielectric_mode;
+  A.suspend_lanes = (desc->reserved > 0 && desc->reserved <= 32) ? desc->reserved : RTB_SUSPEND_LANES;
   A.key = make_uint2((unsigned)(desc->seed & 0xFFFFFFFFull), (unsigned)(desc->seed >> 32));
   A.counters = scene->d_counters;
 }
@@ -667,17 +822,25 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
      * pre-test), 3 megakernel + FP32 sphere pre-test.  See DESIGN.md "Kernel choice". */
     switch (desc->kernel)
     {
+    case 1: /* the first megakernel: if-if walk, 16 warps/SM (kept as the measured baseline) */
+      if (counters) k_render<true, 0><<<blocks, threads, 0, stream>>>(A);
+      else k_render<false, 0><<<blocks, threads, 0, stream>>>(A);
+      break;
     case 2:
       if (counters) k_render_sm<true><<<blocks, threads, 0, stream>>>(A);
       else k_render_sm<false><<<blocks, threads, 0, stream>>>(A);
       break;
     case 3:
-      if (counters) k_render<true, true><<<blocks, threads, 0, stream>>>(A);
-      else k_render<false, true><<<blocks, threads, 0, stream>>>(A);
+      if (counters) k_render<true, 1><<<blocks, threads, 0, stream>>>(A);
+      else k_render<false, 1><<<blocks, threads, 0, stream>>>(A);
       break;
-    default:
-      if (counters) k_render<true, false><<<blocks, threads, 0, stream>>>(A);
-      else k_render<false, false><<<blocks, threads, 0, stream>>>(A);
+    case 5:
+      if (counters) k_render_pw<true><<<blocks, threads, 0, stream>>>(A);
+      else k_render_pw<false><<<blocks, threads, 0, stream>>>(A);
+      break;
+    default: /* 0, 4: while-while walk + select-then-test, 64 registers -> 32 warps/SM */
+      if (counters) k_render<true, 2><<<blocks, threads, 0, stream>>>(A);
+      else k_render<false, 2><<<blocks, threads, 0, stream>>>(A);
       break;
     }
     RTB_CUDA(cudaGetLastError());

@@ -64,7 +64,7 @@ def test_golden_hits_on_device(gpu_api):
     objs = gpu_api.scene_default(320, 180)
     rays = random_rays_in_room(np.random.default_rng(105), 3000)
     with gpu_api.Scene(objs) as sc:
-        for mode in (1, 2, 0):  # BVH, BVH + FP32 pre-test, brute force
+        for mode in (1, 2, 3, 0):  # BVH, BVH + FP32 pre-test, while-while, brute force
             got = sc.trace_rays(rays, use_bvh=mode)
             assert np.array_equal(got["ids"], g["ids"]), mode
             # same double arithmetic without contraction on both sides: bit-identical
@@ -73,7 +73,7 @@ def test_golden_hits_on_device(gpu_api):
             np.testing.assert_allclose(got["uvs"], g["uvs"], rtol=0, atol=1e-15)  # atan2: libm vs CUDA
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 def test_kernel_variants_agree(gpu_api, kernel):
     """megakernel, warp-scheduled state machine and the FP32 pre-test variants compute the
     same per-pixel sums (same lanes, same Philox streams, same exact tests)"""
