@@ -288,7 +288,7 @@ __device__ __forceinline__ bool rayf_walk_setup(const SceneView &sv, const d3 &o
   if (fabsf(dfx) < tiny) dfx = copysignf(tiny, dfx);
   if (fabsf(dfy) < tiny) dfy = copysignf(tiny, dfy);
   if (fabsf(dfz) < tiny) dfz = copysignf(tiny, dfz);
-  rf.idx = 1.0f / dfx; rf.idy = 1.0f / dfy; rf.idz = 1.0f / dfz;
+  rf.idx = __frcp_rn(dfx); rf.idy = __frcp_rn(dfy); rf.idz = __frcp_rn(dfz);
   rf.t_base = 0.0f;
   bool outside = ofx < sv.guard_lo[0] || ofx > sv.guard_hi[0] || ofy < sv.guard_lo[1] ||
                  ofy > sv.guard_hi[1] || ofz < sv.guard_lo[2] || ofz > sv.guard_hi[2];
@@ -324,8 +324,7 @@ __device__ __forceinline__ void rayf_update_tmax(RayF &rf, const HitRec &best)
 
 /* One inner node: tests both children, returns the reference to continue with
  * (RTB_REF_NONE if neither is hit) and pushes the farther one. */
-__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, int *stack_ref,
-                                         float *stack_t, int &sp)
+__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, int2 *stack, int &sp)
 {
   const float4 n0 = __ldg(sv.nodes + 4 * cur + 0);
   const float4 n1 = __ldg(sv.nodes + 4 * cur + 1);
@@ -350,8 +349,7 @@ __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, in
   if (h0 && h1)
   {
     bool swap = c1min < c0min;
-    stack_ref[sp] = swap ? r0 : r1;
-    stack_t[sp] = swap ? c0min : c1min;
+    stack[sp] = make_int2(swap ? r0 : r1, __float_as_int(swap ? c0min : c1min));
     sp++;
     return swap ? r1 : r0;
   }
@@ -361,13 +359,14 @@ __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, in
 }
 
 /* pop the next subtree that can still contain a nearer hit; RTB_REF_NONE when done */
-__device__ __forceinline__ int stack_pop(const RayF &rf, const int *stack_ref, const float *stack_t, int &sp)
+__device__ __forceinline__ int stack_pop(const RayF &rf, const int2 *stack, int &sp)
 {
   while (sp > 0)
   {
     sp--;
-    if (stack_t[sp] <= rf.tmax)
-      return stack_ref[sp];
+    int2 e = stack[sp];
+    if (__int_as_float(e.y) <= rf.tmax)
+      return e.x;
   }
   return RTB_REF_NONE;
 }
@@ -389,8 +388,7 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
 
   if (rayf_walk_setup(sv, o, d, best, rf))
   {
-    int stack_ref[RTB_STACK_SIZE];
-    float stack_t[RTB_STACK_SIZE];
+    int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
     int sp = 0;
     int cur = sv.root_ref;
     while (cur != RTB_REF_NONE)
@@ -398,7 +396,7 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
       if (cur >= 0)
       {
         if (STATS) st.node_visits++;
-        cur = node_step(sv, rf, cur, stack_ref, stack_t, sp);
+        cur = node_step(sv, rf, cur, stack, sp);
         if (cur != RTB_REF_NONE)
           continue;
       }
@@ -411,10 +409,31 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
                              rf.dfy, rf.dfz, rf.o_abs1, best, exact);
         rayf_update_tmax(rf, best);
       }
-      cur = stack_pop(rf, stack_ref, stack_t, sp);
+      cur = stack_pop(rf, stack, sp);
     }
   }
   if (STATS) st.prim_tests += exact;
+}
+
+/* same bound from the FP32 copy of an oversized sphere ({cx,cy,cz,r}, A_c): no FP64->FP32
+ * conversions in the per-ray loop */
+__device__ __forceinline__ bool sphere_lower_bound_f(const float4 c, float Ac, float ofx, float ofy, float ofz,
+                                                     float dfx, float dfy, float dfz, float o_abs1, float &t_lo)
+{
+  float A = (Ac + o_abs1) * 1.0000005f;
+  float e = A * 9.5367431640625e-07f; /* 2^-20 */
+  float eq = 10.0f * A * e;
+  float Lx = c.x - ofx, Ly = c.y - ofy, Lz = c.z - ofz;
+  float tca = fmaf(Lz, dfz, fmaf(Ly, dfy, Lx * dfx));
+  if (tca < -e)
+    return false;
+  float d2 = fmaf(Lz, Lz, fmaf(Ly, Ly, Lx * Lx)) - tca * tca;
+  float disc = fmaf(c.w, c.w, -d2);
+  if (disc < -eq)
+    return false;
+  float thc_hi = sqrtf(fmaxf(disc + eq, 0.0f)) * 1.000001f;
+  t_lo = tca - e - thc_hi;
+  return true;
 }
 
 /* oversized list, "select, then test": an FP32 lower bound per sphere picks the most
@@ -425,28 +444,37 @@ __device__ __forceinline__ void big_list_select_test(const SceneView &sv, const 
 {
   if (sv.n_big <= 0)
     return;
-  float tlo_min = 3.0e38f;
+  const float4 *fcopy = sv.big + 3 * sv.n_big;
+  float tlo_min = 3.0e38f, tlo_second = 3.0e38f;
   int kmin = -1;
   unsigned mask = 0u;
   for (int k = 0; k < sv.n_big; k++)
   {
     float tlo;
-    if (sphere_lower_bound(load_prim(sv.big, k), rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy, rf.dfz, rf.o_abs1, tlo))
+    const float4 c = __ldg(fcopy + 2 * k);
+    const float Ac = __ldg(fcopy + 2 * k + 1).x;
+    if (sphere_lower_bound_f(c, Ac, rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy, rf.dfz, rf.o_abs1, tlo))
     {
       mask |= 1u << k;
       if (tlo < tlo_min)
       {
+        tlo_second = tlo_min;
         tlo_min = tlo;
         kmin = k;
       }
+      else
+        tlo_second = fminf(tlo_second, tlo);
     }
   }
-  if (kmin >= 0)
-  {
-    test_prim(load_prim(sv.big, kmin), ~kmin, o, d, best);
-    exact++;
-    mask &= ~(1u << kmin);
-  }
+  if (kmin < 0)
+    return;
+  test_prim(load_prim(sv.big, kmin), ~kmin, o, d, best);
+  exact++;
+  mask &= ~(1u << kmin);
+  /* nobody else can win if even the second-smallest lower bound exceeds the result */
+  float best_up = best.t >= 1e30 ? 3.0e38f : __double2float_ru(best.t) * 1.0000005f;
+  if (tlo_second > best_up)
+    return;
   while (mask)
   {
     int k = __ffs(mask) - 1;
@@ -477,8 +505,7 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
 
   if (rayf_walk_setup(sv, o, d, best, rf))
   {
-    int stack_ref[RTB_STACK_SIZE];
-    float stack_t[RTB_STACK_SIZE];
+    int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
     int sp = 0;
     int cur = sv.root_ref;
     while (cur != RTB_REF_NONE)
@@ -486,8 +513,8 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
       while (cur >= 0 && cur != RTB_REF_NONE)
       {
         if (STATS) st.node_visits++;
-        int nxt = node_step(sv, rf, cur, stack_ref, stack_t, sp);
-        cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack_ref, stack_t, sp);
+        int nxt = node_step(sv, rf, cur, stack, sp);
+        cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
       }
       if (cur == RTB_REF_NONE)
         break;
@@ -497,7 +524,7 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
         test_prim_filtered<false>(load_prim(sv.prims, first + k), first + k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx,
                                   rf.dfy, rf.dfz, rf.o_abs1, best, exact);
       rayf_update_tmax(rf, best);
-      cur = stack_pop(rf, stack_ref, stack_t, sp);
+      cur = stack_pop(rf, stack, sp);
     }
   }
   if (STATS) st.prim_tests += exact;

@@ -109,7 +109,11 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
      * The reference traces both; here one is chosen with p = clamp(kr, .05, .95) and
      * weighted kr/p or kt/(1-p) -- the same expectation. */
     double facing = -d3_dot(st.d, s.normal);
-    double fresnel = __dadd_rn(__dmul_rn(1.0, 0.1), __dmul_rn(pow(__dsub_rn(1.0, facing), 3.0), __dsub_rn(1.0, 0.1)));
+    /* mix(pow(1 - facing, 3), 1, 0.1) (raytracer.c:518); x*x*x differs from libm pow(x, 3) by
+     * at most 1 ulp, and only scales a colour weight (never geometry) */
+    double omf = __dsub_rn(1.0, facing);
+    double cube = __dmul_rn(__dmul_rn(omf, omf), omf);
+    double fresnel = __dadd_rn(__dmul_rn(1.0, 0.1), __dmul_rn(cube, __dsub_rn(1.0, 0.1)));
     double kr = fresnel;
     double kt = __dmul_rn(__dsub_rn(1.0, fresnel), 1.0);
     double p = kr < 0.05 ? 0.05 : (kr > 0.95 ? 0.95 : kr);
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(128, WALK == 2 ? 8 : 4) k_render(const __grid_
 enum { MODE_NODE = 0, MODE_PRIM = 1, MODE_SHADE = 2, MODE_IDLE = 3 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_render_sm(const __grid_constant__ RenderArgs A)
+__global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ RenderArgs A)
 {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -296,8 +300,7 @@ __global__ void __launch_bounds__(128) k_render_sm(const __grid_constant__ Rende
   HitRec best;
   best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
   RayF rf;
-  int stack_ref[RTB_STACK_SIZE];
-  float stack_t[RTB_STACK_SIZE];
+  int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
   int sp = 0;
   int cur = 0, prim_i = 0, prim_end = 0;
   bool big_phase = false;
@@ -361,9 +364,9 @@ __global__ void __launch_bounds__(128) k_render_sm(const __grid_constant__ Rende
         for (int it = 0; it < RTB_NODE_BURST && mode == MODE_NODE; it++)
         {
           if (STATS) ts.node_visits++;
-          int nxt = node_step(A.sv, rf, cur, stack_ref, stack_t, sp);
+          int nxt = node_step(A.sv, rf, cur, stack, sp);
           if (nxt == RTB_REF_NONE)
-            nxt = stack_pop(rf, stack_ref, stack_t, sp);
+            nxt = stack_pop(rf, stack, sp);
           set_cur(nxt);
         }
       }
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(128) k_render_sm(const __grid_constant__ Rende
           else
           {
             rayf_update_tmax(rf, best);
-            set_cur(stack_pop(rf, stack_ref, stack_t, sp));
+            set_cur(stack_pop(rf, stack, sp));
           }
         }
       }
@@ -485,8 +488,7 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
   best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
   RayF rf;
   rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
-  int stack_ref[RTB_STACK_SIZE];
-  float stack_t[RTB_STACK_SIZE];
+  int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
   int sp = 0;
   int cur = RTB_REF_NONE;
   bool walking = false;
@@ -532,26 +534,36 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
       const unsigned bwait = __ballot_sync(0xFFFFFFFFu, st.alive && !walking);
       if (bwait != 0u && __popc(bw) < A.suspend_lanes)
         break;
-      if (walking)
+      /* node phase: inner nodes only; ends as soon as fewer than half of the walkers are
+       * still at inner nodes (the others wait with a leaf or a finished query) */
+      const int n_walk = __popc(bw);
+      while (true)
       {
-        while (cur >= 0 && cur != RTB_REF_NONE)
+        const bool at_node = walking && cur >= 0 && cur != RTB_REF_NONE;
+        const unsigned bnode = __ballot_sync(0xFFFFFFFFu, at_node);
+        if (bnode == 0u || 2 * __popc(bnode) < n_walk)
+          break;
+        if (at_node)
         {
           if (STATS) ts.node_visits++;
-          int nxt = node_step(A.sv, rf, cur, stack_ref, stack_t, sp);
-          cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack_ref, stack_t, sp);
+          int nxt = node_step(A.sv, rf, cur, stack, sp);
+          cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+          if (cur == RTB_REF_NONE)
+            walking = false;
         }
-        if (cur != RTB_REF_NONE)
+      }
+      /* leaf phase */
+      if (walking && cur < 0)
+      {
+        int code = ~cur;
+        int first = code >> 3, count = (code & 7) + 1;
+        for (int k = 0; k < count; k++)
         {
-          int code = ~cur;
-          int first = code >> 3, count = (code & 7) + 1;
-          for (int k = 0; k < count; k++)
-          {
-            test_prim(load_prim(A.sv.prims, first + k), first + k, st.o, st.d, best);
-            if (STATS) ts.prim_tests++;
-          }
-          rayf_update_tmax(rf, best);
-          cur = stack_pop(rf, stack_ref, stack_t, sp);
+          test_prim(load_prim(A.sv.prims, first + k), first + k, st.o, st.d, best);
+          if (STATS) ts.prim_tests++;
         }
+        rayf_update_tmax(rf, best);
+        cur = stack_pop(rf, stack, sp);
         if (cur == RTB_REF_NONE)
           walking = false;
       }

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -61,12 +62,21 @@ __device__ __forceinline__ float4 pack_double2(double a, double b)
 }
 
 __global__ void k_marshal_spheres(const SphereIn *__restrict__ in, int n, PrimRec *__restrict__ out,
-                                  float4 *__restrict__ box_lo, float4 *__restrict__ box_hi)
+                                  float4 *__restrict__ box_lo, float4 *__restrict__ box_hi,
+                                  float4 *__restrict__ fp32_copy)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   SphereIn s = in[i];
+  if (fp32_copy)
+  {
+    /* FP32 view for the conservative pre-test of the oversized list (rtb_device.cuh):
+     * {cx, cy, cz, r} and A_c = |c|_1 + r, rounded up */
+    float cx = (float)s.cx, cy = (float)s.cy, cz = (float)s.cz, r = (float)s.r;
+    fp32_copy[2 * i + 0] = make_float4(cx, cy, cz, r);
+    fp32_copy[2 * i + 1] = make_float4((fabsf(cx) + fabsf(cy) + fabsf(cz) + fabsf(r)) * 1.0000005f, 0.0f, 0.0f, 0.0f);
+  }
   PrimRec r;
   r.a = pack_double2(s.cx, s.cy);
   r.b = pack_double2(s.cz, s.r);
@@ -346,14 +356,14 @@ __global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restri
                        const float4 *__restrict__ box_hi, int n, const int2 *__restrict__ children,
                        const int *__restrict__ range_first, const float4 *__restrict__ node_lo,
                        const float4 *__restrict__ node_hi, const BuildParams *__restrict__ bp,
-                       float4 *__restrict__ out_nodes, int *__restrict__ emitted)
+                       float4 *__restrict__ out_nodes, int *__restrict__ emitted, int leaf_max)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1)
     return;
   const float pad = bp->pad;
   int count = __float_as_int(node_lo[i].w);
-  if (count <= RTB_LEAF_MAX)
+  if (count <= leaf_max)
     return;
   int2 ch = children[i];
   float4 lo[2], hi[2];
@@ -374,7 +384,7 @@ __global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restri
       lo[k] = node_lo[c[k]];
       hi[k] = node_hi[c[k]];
       int cc = __float_as_int(lo[k].w);
-      ref[k] = (cc <= RTB_LEAF_MAX) ? leaf_ref(range_first[c[k]], cc) : c[k];
+      ref[k] = (cc <= leaf_max) ? leaf_ref(range_first[c[k]], cc) : c[k];
     }
   }
   out_nodes[4 * (size_t)i + 0] = make_float4(lo[0].x - pad, hi[0].x + pad, lo[0].y - pad, hi[0].y + pad);
@@ -552,7 +562,10 @@ std::vector<char> choose_big(const HostScene &hs)
   std::vector<double> sorted = sizes;
   std::nth_element(sorted.begin(), sorted.begin() + (sorted.size() - 1) / 2, sorted.end());
   double median = sorted[(sorted.size() - 1) / 2];
-  double threshold = 32.0 * median;
+  double ratio = 32.0;
+  if (const char *e = getenv("RTB_BIG_RATIO"))
+    ratio = atof(e);
+  double threshold = ratio * median;
   std::vector<std::pair<double, size_t>> cand;
   for (size_t i = 0; i < hs.spheres.size(); i++)
     if (std::fabs(hs.spheres[i].r) > threshold || !std::isfinite(hs.spheres[i].r))
@@ -582,6 +595,12 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   RTB_CUDA(cudaEventCreate(&ev1));
   RTB_CUDA(cudaEventRecord(ev0, 0));
 
+  /* development knobs (documented in DESIGN.md): leaf size and oversized-primitive ratio */
+  /* measured on B200 (profiles/r1_tuning.md): sphere scenes are fastest with one sphere per
+   * leaf (the exact test is cheap to skip, a leaf visit is not), meshes with two triangles */
+  int leaf_max = hs.meshes.empty() ? 1 : 2;
+  if (const char *e = getenv("RTB_LEAF_MAX"))
+    leaf_max = std::max(1, std::min(8, atoi(e)));
   std::vector<char> big = choose_big(hs);
   std::vector<SphereIn> big_spheres, bvh_spheres;
   for (size_t i = 0; i < hs.spheres.size(); i++)
@@ -605,13 +624,15 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     RTB_CUDA(cudaMemcpyAsync(sc->d_mats, hs.mats.data(), sizeof(float4) * hs.mats.size(), cudaMemcpyHostToDevice, 0));
   dev_bytes += sizeof(float4) * hs.mats.size();
   RTB_CUDA(pool_alloc(&sc->d_counters, 8));
-  RTB_CUDA(pool_alloc(&sc->d_big, 3 * std::max<size_t>(1, big_spheres.size())));
+  /* 3 float4 per record, followed by 2 float4 per FP32 copy */
+  RTB_CUDA(pool_alloc(&sc->d_big, 5 * std::max<size_t>(1, big_spheres.size())));
   DevBuf<SphereIn> d_big_in, d_bvh_in;
   if (!big_spheres.empty())
   {
     RTB_CUDA(d_big_in.alloc(big_spheres.size()));
     RTB_CUDA(cudaMemcpyAsync(d_big_in.p, big_spheres.data(), sizeof(SphereIn) * big_spheres.size(), cudaMemcpyHostToDevice, 0));
-    k_marshal_spheres<<<1, 32>>>(d_big_in.p, (int)big_spheres.size(), reinterpret_cast<PrimRec *>(sc->d_big), nullptr, nullptr);
+    k_marshal_spheres<<<1, 32>>>(d_big_in.p, (int)big_spheres.size(), reinterpret_cast<PrimRec *>(sc->d_big), nullptr, nullptr,
+                                 sc->d_big + 3 * big_spheres.size());
     RTB_CUDA(cudaGetLastError());
   }
   dev_bytes += sizeof(PrimRec) * big_spheres.size();
@@ -662,7 +683,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     {
       RTB_CUDA(d_bvh_in.alloc(n_bs));
       RTB_CUDA(cudaMemcpyAsync(d_bvh_in.p, bvh_spheres.data(), sizeof(SphereIn) * n_bs, cudaMemcpyHostToDevice, 0));
-      k_marshal_spheres<<<(int)((n_bs + T - 1) / T), T>>>(d_bvh_in.p, (int)n_bs, d_unsorted.p, d_lo.p, d_hi.p);
+      k_marshal_spheres<<<(int)((n_bs + T - 1) / T), T>>>(d_bvh_in.p, (int)n_bs, d_unsorted.p, d_lo.p, d_hi.p, nullptr);
       RTB_CUDA(cudaGetLastError());
     }
     {
@@ -705,7 +726,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     if (want_tex)
       RTB_CUDA(pool_alloc(&sc->d_tex, 3 * N));
 
-    if (N <= RTB_LEAF_MAX)
+    if ((int)N <= leaf_max)
     {
       /* a single leaf; order = insertion order */
       RTB_CUDA(cudaMemcpyAsync(sc->d_prims, d_unsorted.p, sizeof(PrimRec) * N, cudaMemcpyDeviceToDevice, 0));
@@ -750,7 +771,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       RTB_CUDA(pool_alloc(&sc->d_nodes, 4 * (N - 1)));
       RTB_CUDA(cudaMemsetAsync(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1), 0));
       k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
-                            d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1);
+                            d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1, leaf_max);
       RTB_CUDA(cudaGetLastError());
       k_reorder<<<blocks, T>>>(d_vals_sorted.p, (int)N, d_unsorted.p, reinterpret_cast<PrimRec *>(sc->d_prims),
                                want_tex ? d_tex_unsorted.p : nullptr, sc->d_tex);
