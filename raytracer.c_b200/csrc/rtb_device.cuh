@@ -322,9 +322,31 @@ __device__ __forceinline__ void rayf_update_tmax(RayF &rf, const HitRec &best)
     rf.tmax = __double2float_ru(best.t - (double)rf.t_base) * RTB_WIDEN;
 }
 
+/* Traversal stack.  The first SD entries of every thread live in shared memory, laid out
+ * [entry][thread] (conflict-free), the rest in local memory.  SD = 0 keeps everything in
+ * local memory.  Entry = {reference, entry distance as float bits}. */
+template <int SD>
+struct WalkStack
+{
+  int2 *smem;  /* this thread's column: entry k at smem[k * blockDim.x]; unused when SD == 0 */
+  int2 *local; /* RTB_STACK_SIZE entries */
+  int stride;
+  __device__ __forceinline__ void put(int sp, int2 e) const
+  {
+    if (SD > 0 && sp < SD) smem[sp * stride] = e;
+    else local[sp - SD] = e;
+  }
+  __device__ __forceinline__ int2 get(int sp) const
+  {
+    if (SD > 0 && sp < SD) return smem[sp * stride];
+    return local[sp - SD];
+  }
+};
+
 /* One inner node: tests both children, returns the reference to continue with
  * (RTB_REF_NONE if neither is hit) and pushes the farther one. */
-__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, int2 *stack, int &sp)
+template <int SD>
+__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
 {
   const float4 n0 = __ldg(sv.nodes + 4 * cur + 0);
   const float4 n1 = __ldg(sv.nodes + 4 * cur + 1);
@@ -349,7 +371,7 @@ __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, in
   if (h0 && h1)
   {
     bool swap = c1min < c0min;
-    stack[sp] = make_int2(swap ? r0 : r1, __float_as_int(swap ? c0min : c1min));
+    stack.put(sp, make_int2(swap ? r0 : r1, __float_as_int(swap ? c0min : c1min)));
     sp++;
     return swap ? r1 : r0;
   }
@@ -359,12 +381,13 @@ __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, in
 }
 
 /* pop the next subtree that can still contain a nearer hit; RTB_REF_NONE when done */
-__device__ __forceinline__ int stack_pop(const RayF &rf, const int2 *stack, int &sp)
+template <int SD>
+__device__ __forceinline__ int stack_pop(const RayF &rf, const WalkStack<SD> &stack, int &sp)
 {
   while (sp > 0)
   {
     sp--;
-    int2 e = stack[sp];
+    int2 e = stack.get(sp);
     if (__int_as_float(e.y) <= rf.tmax)
       return e.x;
   }
@@ -388,7 +411,8 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
 
   if (rayf_walk_setup(sv, o, d, best, rf))
   {
-    int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
+    int2 stack_mem[RTB_STACK_SIZE];
+    WalkStack<0> stack = { nullptr, stack_mem, 0 };
     int sp = 0;
     int cur = sv.root_ref;
     while (cur != RTB_REF_NONE)
@@ -490,9 +514,9 @@ __device__ __forceinline__ void big_list_select_test(const SceneView &sv, const 
  * (profiles/r1_c3_megakernel_ncu.md).  The oversized list is handled "select, then test":
  * an FP32 lower bound per sphere picks the most promising one, which is tested exactly by
  * all lanes at once; the few others whose bound still beats the result follow. */
-template <bool STATS>
+template <bool STATS, int SD>
 __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best,
-                                               TraceStats &st)
+                                               TraceStats &st, int2 *smem_column, int smem_stride)
 {
   best.t = DBL_MAX;
   best.gid = 0x7FFFFFFF;
@@ -505,7 +529,8 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
 
   if (rayf_walk_setup(sv, o, d, best, rf))
   {
-    int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
+    int2 stack_mem[RTB_STACK_SIZE - SD];
+    WalkStack<SD> stack = { smem_column, stack_mem, smem_stride };
     int sp = 0;
     int cur = sv.root_ref;
     while (cur != RTB_REF_NONE)

@@ -45,6 +45,10 @@ struct PathCounters
   unsigned rays, rays_hit;
 };
 
+#ifndef RTB_SMEM_STACK
+#define RTB_SMEM_STACK 8 /* stack entries per thread kept in shared memory (default kernel) */
+#endif
+
 #define RT_BACKGROUND (10.0f / 255.0f) /* raytracer.h:46, also returned on a depth cut (quirk Q2) */
 
 __device__ __forceinline__ void path_begin(const RenderArgs &A, PathState &st, int x, int y, unsigned pixel, unsigned sample)
@@ -174,6 +178,9 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
 template <bool STATS, int WALK>
 __global__ void __launch_bounds__(128, WALK == 2 ? 8 : 4) k_render(const __grid_constant__ RenderArgs A)
 {
+  /* top of the traversal stack in shared memory (WALK == 2): keeps the hottest local-memory
+   * traffic out of L1/L2 (profiles/r1_c3_default_ncu.md: 27 GB of local write-back per launch) */
+  __shared__ int2 s_stack[WALK == 2 ? RTB_SMEM_STACK : 1][128];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int tile = warp % A.n_tiles;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(128, WALK == 2 ? 8 : 4) k_render(const __grid_
       pc.rays++;
       pc.rays_hit++;
       if (WALK == 2)
-        closest_hit_ww<STATS>(A.sv, st.o, st.d, best, ts);
+        closest_hit_ww<STATS, RTB_SMEM_STACK>(A.sv, st.o, st.d, best, ts, &s_stack[0][threadIdx.x], 128);
       else
         closest_hit<STATS, WALK == 1>(A.sv, st.o, st.d, best, ts);
       path_shade(A, st, best, pixel, (unsigned)s, sr, sg, sb, pc, nullptr);
@@ -300,7 +307,8 @@ __global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ Re
   HitRec best;
   best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
   RayF rf;
-  int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
+  int2 stack_mem[RTB_STACK_SIZE];
+  WalkStack<0> stack = { nullptr, stack_mem, 0 };
   int sp = 0;
   int cur = 0, prim_i = 0, prim_end = 0;
   bool big_phase = false;
@@ -488,7 +496,8 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
   best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
   RayF rf;
   rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
-  int2 stack[RTB_STACK_SIZE]; /* .x = reference, .y = entry distance (float bits) */
+  int2 stack_mem[RTB_STACK_SIZE];
+  WalkStack<0> stack = { nullptr, stack_mem, 0 };
   int sp = 0;
   int cur = RTB_REF_NONE;
   bool walking = false;
@@ -641,7 +650,7 @@ __global__ void k_trace_rays(const __grid_constant__ SceneView sv, const double 
   HitRec best;
   TraceStats st = { 0u, 0u };
   if (use_bvh == 3)
-    closest_hit_ww<false>(sv, o, d, best, st);
+    closest_hit_ww<false, 0>(sv, o, d, best, st, nullptr, 0);
   else if (use_bvh == 2)
     closest_hit<false, true>(sv, o, d, best, st);
   else if (use_bvh)
