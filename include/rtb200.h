@@ -63,8 +63,13 @@ typedef struct
   int dielectric_mode;          /* RTB_DIELECTRIC_* */
   uint64_t seed;                /* Philox key */
   int kernel;                   /* 0 = auto; 1 megakernel (if-if walk); 2 warp-scheduled state machine;
-                                   3 megakernel + FP32 sphere pre-test; 4 while-while walk; 5 suspendable walk */
-  int reserved;                 /* kernel 5 tuning: suspend threshold in lanes (0 = default) */
+                                   3 megakernel + FP32 sphere pre-test; 4 while-while walk; 5 suspendable walk;
+                                   6 wavefront (ray queues in HBM, persistent trace kernel that refills idle lanes) */
+  int reserved;                 /* tuning: kernel 5 suspend threshold in lanes; kernel 6 refill threshold in idle
+                                   lanes (0 = default) */
+  int planes;                   /* sample sub-ranges accumulated separately and summed in order (fixes the
+                                   floating-point summation order); 0 = auto */
+  int reserved2;
 } rtb_render_desc;
 
 typedef struct

@@ -76,6 +76,8 @@ struct rtb_scene
   float2 *d_tex = nullptr;
   float *d_scratch = nullptr; /* split planes */
   size_t scratch_bytes = 0;
+  void *d_wf = nullptr;       /* wavefront kernels: ray queues + accumulation planes (rtb_wavefront.cu) */
+  size_t wf_bytes = 0;
   unsigned long long *d_counters = nullptr;
   rtb_scene_info info{};
 };

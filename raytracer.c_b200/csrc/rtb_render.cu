@@ -13,166 +13,12 @@
  * key = seed (see rtb_device.cuh and oracle/oracle.c for the layout; both sides must
  * agree word for word).
  */
-#include "rtb_device.cuh"
+#include "rtb_path.cuh"
 
 #include <algorithm>
 #include <vector>
 #include <cstring>
 
-struct RenderArgs
-{
-  SceneView sv;
-  CameraView cam;
-  int width, height, tiles_x, n_tiles;
-  int s_begin, s_end, chunk, splits;
-  int max_depth, dielectric_mode;
-  int suspend_lanes; /* k_render_pw: suspend the walk when fewer lanes than this are walking */
-  uint2 key;
-  float *out; /* [splits][height*width*3] */
-  unsigned long long *counters;
-};
-
-struct PathState
-{
-  d3 o, d;
-  float tr, tg, tb; /* throughput */
-  int depth;
-  bool alive;
-};
-
-struct PathCounters
-{
-  unsigned rays, rays_hit;
-};
-
-#ifndef RTB_SMEM_STACK
-#define RTB_SMEM_STACK 8 /* stack entries per thread kept in shared memory (default kernel) */
-#endif
-
-#define RT_BACKGROUND (10.0f / 255.0f) /* raytracer.h:46, also returned on a depth cut (quirk Q2) */
-
-__device__ __forceinline__ void path_begin(const RenderArgs &A, PathState &st, int x, int y, unsigned pixel, unsigned sample)
-{
-  /* jitter: u = (x + xi1)/(W-1), v = (y + xi2)/(H-1), raytracer.c:203-204 */
-  uint4 w = philox4x32_10(make_uint4(pixel, sample, 0xFFFFFFFFu, 0u), A.key);
-  double u = __ddiv_rn(__dadd_rn((double)x, uniform31(w.x)), __dsub_rn((double)A.width, 1.0));
-  double v = __ddiv_rn(__dadd_rn((double)y, uniform31(w.y)), __dsub_rn((double)A.height, 1.0));
-  camera_ray(A.cam, u, v, st.o, st.d);
-  st.tr = st.tg = st.tb = 1.0f;
-  st.depth = 0;
-  st.alive = true;
-}
-
-/* One vertex of the path: the body of trace_path after the scene query.
- * `sum` accumulates throughput * (emission | background). */
-__device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, const HitRec &best, unsigned pixel,
-                                           unsigned sample, float &sr, float &sg, float &sb, PathCounters &pc,
-                                           Surface *surf_out)
-{
-  if (best.t >= 1e300)
-  {
-    sr += st.tr * RT_BACKGROUND; sg += st.tg * RT_BACKGROUND; sb += st.tb * RT_BACKGROUND;
-    st.alive = false;
-    return;
-  }
-  /* material first: uv is only needed for checkered objects */
-  int slot_obj;
-  {
-    const float4 *rec = best.slot >= 0 ? A.sv.prims + 3 * best.slot : A.sv.big + 3 * (~best.slot);
-    slot_obj = (int)(__float_as_uint(__ldg(rec + 2).z) & 0x7FFFFFFFu);
-  }
-  const float4 m0 = __ldg(A.sv.mats + 2 * slot_obj + 0);
-  const float4 m1 = __ldg(A.sv.mats + 2 * slot_obj + 1);
-  const unsigned flags = __float_as_uint(m1.w);
-  Surface s = surface_at(A.sv, st.o, st.d, best, (flags & RT_M_CHECKERED) != 0);
-  if (surf_out)
-    *surf_out = s;
-
-  /* emission is added whether or not the path survives (raytracer.c:502,553) */
-  sr += st.tr * m1.x; sg += st.tg * m1.y; sb += st.tb * m1.z;
-
-  /* Russian roulette, one draw per vertex (raytracer.c:497-502) */
-  const unsigned bounce_word = (unsigned)st.depth | 0x100u;
-  uint4 w = philox4x32_10(make_uint4(pixel, sample, bounce_word, 0u), A.key);
-  if ((w.x >> 1) >= __float_as_uint(m0.w))
-  {
-    st.alive = false;
-    return;
-  }
-  st.tr *= m0.x; st.tg *= m0.y; st.tb *= m0.z; /* albedo / prob */
-  if (flags & RT_M_CHECKERED)
-  {
-    float c = checker_factor(s.u, s.v, 100000.0); /* raytracer.c:508 */
-    st.tr *= c; st.tg *= c; st.tb *= c;
-  }
-
-  if (flags & RT_M_REFRACTION)
-  {
-    /* raytracer.c:514-529.  refract(-d, n, 1.0) returns -d (quirk Q3), so the "refracted"
-     * ray is the retro-ray normalize(-d); the reflected one is normalize(reflect(d, n)).
-     * The reference traces both; here one is chosen with p = clamp(kr, .05, .95) and
-     * weighted kr/p or kt/(1-p) -- the same expectation. */
-    double facing = -d3_dot(st.d, s.normal);
-    /* mix(pow(1 - facing, 3), 1, 0.1) (raytracer.c:518); x*x*x differs from libm pow(x, 3) by
-     * at most 1 ulp, and only scales a colour weight (never geometry) */
-    double omf = __dsub_rn(1.0, facing);
-    double cube = __dmul_rn(__dmul_rn(omf, omf), omf);
-    double fresnel = __dadd_rn(__dmul_rn(1.0, 0.1), __dmul_rn(cube, __dsub_rn(1.0, 0.1)));
-    double kr = fresnel;
-    double kt = __dmul_rn(__dsub_rn(1.0, fresnel), 1.0);
-    double p = kr < 0.05 ? 0.05 : (kr > 0.95 ? 0.95 : kr);
-    float wgt;
-    if (uniform31(w.y) < p)
-    {
-      st.d = d3_normalize(reflect_dir(d3_scale(st.d, 1.0), s.normal));
-      wgt = (float)__ddiv_rn(kr, p);
-    }
-    else
-    {
-      st.d = d3_normalize(d3_scale(st.d, -1.0));
-      wgt = (float)__ddiv_rn(kt, __dsub_rn(1.0, p));
-    }
-    st.tr *= wgt; st.tg *= wgt; st.tb *= wgt;
-  }
-  else if (flags & RT_M_REFLECTION)
-  {
-    st.d = reflect_dir(st.d, s.normal); /* not renormalised (quirk Q8) */
-  }
-  else
-  {
-    /* uniform direction by cube rejection, flipped into the normal's hemisphere; weight
-     * cos(theta), no pdf (raytracer.c:231-253,545-551; quirk Q5) */
-    d3 p;
-    unsigned k = 0;
-    uint4 r = w;
-    double px = uniform31(r.y), py = uniform31(r.z), pz = uniform31(r.w);
-    while (true)
-    {
-      p = d3_make(__dadd_rn(__dmul_rn(px, 2.0), -1.0), __dadd_rn(__dmul_rn(py, 2.0), -1.0),
-                  __dadd_rn(__dmul_rn(pz, 2.0), -1.0));
-      if (!(d3_length(p) > 1.0) || k >= 98u)
-        break;
-      k++;
-      r = philox4x32_10(make_uint4(pixel, sample, bounce_word, k), A.key);
-      px = uniform31(r.x); py = uniform31(r.y); pz = uniform31(r.z);
-    }
-    d3 dir = d3_normalize(p);
-    if (d3_dot(dir, s.normal) < 0)
-      dir = d3_scale(dir, -1.0);
-    float c = (float)d3_dot(dir, s.normal);
-    st.d = dir;
-    st.tr *= c; st.tg *= c; st.tb *= c;
-  }
-  st.o = s.point;
-  st.depth++;
-  if (st.depth > A.max_depth)
-  {
-    /* the next trace_path call returns BACKGROUND without intersecting (raytracer.c:487) */
-    pc.rays++;
-    sr += st.tr * RT_BACKGROUND; sg += st.tg * RT_BACKGROUND; sb += st.tb * RT_BACKGROUND;
-    st.alive = false;
-  }
-}
 
 /* WALK: 0 = if-if loop, 1 = if-if + FP32 sphere pre-test, 2 = while-while + select-then-test */
 template <bool STATS, int WALK>
@@ -740,9 +586,9 @@ static int check_desc(const rtb_render_desc *d)
     rtb_set_error("rtb_render_desc: need width,height >= 2, sample_end >= sample_begin, 0 <= max_depth <= 255");
     return RTB_EINVAL;
   }
-  if (d->kernel < 0 || d->kernel > 5)
+  if (d->kernel < 0 || d->kernel > 6)
   {
-    rtb_set_error("rtb_render_desc.kernel: 0 auto, 1 megakernel, 2 warp-scheduled, 3 megakernel + pre-test");
+    rtb_set_error("rtb_render_desc.kernel: 0 auto, 1..5 megakernel variants, 6 wavefront");
     return RTB_EINVAL;
   }
   if (d->dielectric_mode != RTB_DIELECTRIC_STOCHASTIC)
@@ -794,9 +640,17 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   fill_args(A, scene, camera12, desc);
   const int spp = desc->sample_end - desc->sample_begin;
   const size_t n_px = (size_t)desc->width * desc->height;
-  /* enough threads to fill 148 SMs a few times over even for small frames */
-  const long long want_threads = 148ll * 2048 * 2;
+  /* Planes: the call's samples are cut into `splits` contiguous sub-ranges that are accumulated
+   * separately and summed in order -- this fixes the floating-point summation order, so every
+   * kernel variant gives the same bits for the same number of planes.
+   * Megakernels: enough threads to fill 148 SMs a few times over even for small frames.
+   * Wavefront: ~8 M paths in flight per wave (1.4 GB of queues), so the deep bounces still have
+   * enough rays to fill the machine. */
+  const bool wavefront = desc->kernel == 6;
+  const long long want_threads = wavefront ? (8ll << 20) : 148ll * 2048 * 2;
   int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);
+  if (desc->planes > 0)
+    splits = std::min(desc->planes, 1024);
   splits = std::max(1, std::min(splits, spp));
   int chunk = spp > 0 ? (spp + splits - 1) / splits : 0;
   if (chunk > 0)
@@ -820,6 +674,14 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   }
   else
   {
+    if (wavefront)
+    {
+      int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr, launches);
+      if (wrc != RTB_OK)
+        return wrc;
+    }
+    else
+    {
     if (splits > 1)
     {
       size_t need = sizeof(float) * 3 * n_px * splits;
@@ -872,6 +734,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
       k_sum_planes<<<(int)((n + 255) / 256), 256, 0, stream>>>(scene->d_scratch, splits, n, d_accum);
       RTB_CUDA(cudaGetLastError());
       launches++;
+    }
     }
   }
 

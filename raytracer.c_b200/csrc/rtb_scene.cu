@@ -895,7 +895,7 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
   /* stream-ordered: the memory goes back to the pool once work queued before this point on
    * the legacy default stream (which synchronises with every blocking stream) is done */
   void *bufs[] = { scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_tex,
-                   scene->d_scratch, scene->d_counters };
+                   scene->d_scratch, scene->d_counters, scene->d_wf };
   for (void *b : bufs)
     if (b)
       cudaFreeAsync(b, 0);

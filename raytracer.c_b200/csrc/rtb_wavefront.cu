@@ -1,0 +1,425 @@
+/*
+ * rtb_wavefront.cu -- the wavefront form of render() (raytracer.c:176-223).
+ *
+ * Why it exists (profiles/r1_c3_default_ncu.md): in the megakernel a warp's 32 lanes each own
+ * one path; after the first bounce the rays are incoherent and traversal lengths have a long
+ * tail, so the warp waits for its slowest ray at every bounce -- 4 of 32 lanes were walking
+ * on average.  Here a bounce is split in two kernels that exchange rays through queues in HBM:
+ *
+ *   k_wf_generate  camera samples (raytracer.c:203-209)                    -> queue[0]
+ *   k_wf_trace     nearest hit for every queued ray.  PERSISTENT: a lane that finishes its
+ *                  ray does not wait for its neighbours -- as soon as enough lanes are idle
+ *                  the warp refills them from the queue (Aila & Laine's "replace terminated
+ *                  rays", made cheap because a ray is one 64-byte read, not a shading pass)
+ *   k_wf_shade     the body of trace_path after the scene query (raytracer.c:492-553) with all
+ *                  lanes busy; survivors are appended to the next queue by warp-aggregated
+ *                  atomics (ballot + one atomicAdd per warp)
+ *
+ * Queue entry = 80 bytes in five 16-byte SoA arrays (coalesced): origin and direction as
+ * doubles, {path id, throughput}, and the hit record {t, gid, slot}.  The oversized-sphere
+ * list is tested by the producer (all lanes busy), so the hit record arrives pre-seeded.
+ *
+ * Determinism: a path slot (plane, pixel) carries exactly one path per wave, so its float4
+ * accumulator is read-modify-written by one thread at a time in vertex order -- the same
+ * sequence of additions the megakernel performs in registers.  Queue ORDER depends on atomics,
+ * results do not.  Sums are bit-identical to the megakernel's for the same number of planes.
+ */
+#include "rtb_path.cuh"
+
+#include <algorithm>
+
+#define WF_FULL 0xFFFFFFFFu
+#ifndef WF_SMEM_STACK
+#define WF_SMEM_STACK 8
+#endif
+#ifndef WF_TRACE_BLOCKS_PER_SM
+#define WF_TRACE_BLOCKS_PER_SM 8
+#endif
+
+struct WfQueue
+{
+  double2 *o_xy;  /* origin.x, origin.y */
+  double2 *oz_dx; /* origin.z, direction.x */
+  double2 *d_yz;  /* direction.y, direction.z */
+  uint4 *path;    /* path slot id, throughput r, g, b (float bits) */
+  uint4 *hit;     /* best.t (two words), gid, slot */
+};
+
+struct WfCounters
+{
+  unsigned long long *totals; /* scene->d_counters: rays, rays_hit, prim_tests, node_visits, paths */
+};
+
+__device__ __forceinline__ uint4 pack_hit(const HitRec &h)
+{
+  return make_uint4((unsigned)__double2loint(h.t), (unsigned)__double2hiint(h.t), (unsigned)h.gid, (unsigned)h.slot);
+}
+
+__device__ __forceinline__ HitRec unpack_hit(const uint4 v)
+{
+  HitRec h;
+  h.t = __hiloint2double((int)v.y, (int)v.x);
+  h.gid = (int)v.z;
+  h.slot = (int)v.w;
+  return h;
+}
+
+/* the part of the scene query that does not walk the tree: oversized primitives */
+__device__ __forceinline__ void ray_seed_hit(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best, unsigned &exact)
+{
+  best.t = DBL_MAX;
+  best.gid = 0x7FFFFFFF;
+  best.slot = 0;
+  RayF rf;
+  rayf_basic(o, d, rf);
+  big_list_select_test(sv, o, d, rf, best, exact);
+}
+
+/* warp-aggregated append: every lane of the warp must call this */
+__device__ __forceinline__ void wf_enqueue(const WfQueue &q, unsigned *count, bool want, int lane, const d3 &o, const d3 &d,
+                                           unsigned pid, float tr, float tg, float tb, const HitRec &seed)
+{
+  const unsigned m = __ballot_sync(WF_FULL, want);
+  if (m == 0u)
+    return;
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader)
+    base = atomicAdd(count, (unsigned)__popc(m));
+  base = __shfl_sync(WF_FULL, base, leader);
+  if (want)
+  {
+    const unsigned i = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+    q.o_xy[i] = make_double2(o.x, o.y);
+    q.oz_dx[i] = make_double2(o.z, d.x);
+    q.d_yz[i] = make_double2(d.y, d.z);
+    q.path[i] = make_uint4(pid, __float_as_uint(tr), __float_as_uint(tg), __float_as_uint(tb));
+    q.hit[i] = pack_hit(seed);
+  }
+}
+
+__device__ __forceinline__ void wf_add_counters(unsigned long long *totals, int lane, unsigned long long c0,
+                                                unsigned long long c1, unsigned long long c2, unsigned long long c3,
+                                                unsigned long long c4)
+{
+  for (int off = 16; off > 0; off >>= 1)
+  {
+    c0 += __shfl_xor_sync(WF_FULL, c0, off);
+    c1 += __shfl_xor_sync(WF_FULL, c1, off);
+    c2 += __shfl_xor_sync(WF_FULL, c2, off);
+    c3 += __shfl_xor_sync(WF_FULL, c3, off);
+    c4 += __shfl_xor_sync(WF_FULL, c4, off);
+  }
+  if (lane == 0)
+  {
+    if (c0) atomicAdd(&totals[0], c0);
+    if (c1) atomicAdd(&totals[1], c1);
+    if (c2) atomicAdd(&totals[2], c2);
+    if (c3) atomicAdd(&totals[3], c3);
+    if (c4) atomicAdd(&totals[4], c4);
+  }
+}
+
+/* ---- camera samples of one wave ------------------------------------------------------------
+ * One thread per path slot; warps map to 8x4 pixel tiles of one plane so that the primary
+ * rays a warp appends (and a trace warp later fetches together) are coherent. */
+__global__ void __launch_bounds__(128) k_wf_generate(const __grid_constant__ RenderArgs A, int wave, WfQueue q,
+                                                     unsigned *count)
+{
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int tile = (int)(warp % A.n_tiles);
+  const int plane = (int)(warp / A.n_tiles);
+  const int x = (tile % A.tiles_x) * 8 + (lane & 7);
+  const int y = (tile / A.tiles_x) * 4 + (lane >> 3);
+  const int s = A.s_begin + plane * A.chunk + wave;
+  const bool valid = x < A.width && y < A.height && plane < A.splits && s < min(A.s_end, A.s_begin + (plane + 1) * A.chunk);
+  const unsigned pixel = (unsigned)(y * A.width + x);
+
+  PathState st;
+  st.o = d3_make(0, 0, 0);
+  st.d = d3_make(0, 0, 1);
+  st.tr = st.tg = st.tb = 1.0f;
+  HitRec seed;
+  seed.t = DBL_MAX; seed.gid = 0x7FFFFFFF; seed.slot = 0;
+  unsigned exact = 0;
+  if (valid)
+  {
+    path_begin(A, st, x, y, pixel, (unsigned)s);
+    ray_seed_hit(A.sv, st.o, st.d, seed, exact);
+  }
+  const unsigned pid = (unsigned)plane * (unsigned)(A.width * A.height) + pixel;
+  wf_enqueue(q, count, valid, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed);
+  wf_add_counters(A.counters, lane, 0ull, 0ull, exact, 0ull, valid ? 1ull : 0ull);
+}
+
+/* ---- nearest hit for a whole queue -----------------------------------------------------------
+ * Persistent warps.  Each warp grabs batches of consecutive rays (one atomic per batch) and
+ * keeps its lanes supplied from the batch: whenever `refill_idle` or more lanes have no ray,
+ * the walk is interrupted and the idle lanes load the next rays.  The walk itself is the
+ * while-while loop of closest_hit_ww (inner nodes until every lane has reached a leaf, then
+ * the exact FP64 leaf tests together). */
+template <bool STATS>
+__global__ void __launch_bounds__(128, WF_TRACE_BLOCKS_PER_SM)
+k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
+           unsigned long long *totals, int refill_idle)
+{
+  __shared__ int2 s_stack[WF_SMEM_STACK][128];
+  const int lane = threadIdx.x & 31;
+  const unsigned n = *n_ptr;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  /* batch: large enough to make the atomic rare, small enough that every warp gets work */
+  unsigned batch = (n / (n_warps * 4u)) & ~31u;
+  batch = batch < 32u ? 32u : (batch > 512u ? 512u : batch);
+
+  unsigned next = 0, end = 0; /* the warp's current batch, warp-uniform */
+  bool pool_empty = n == 0u;
+
+  bool active = false;
+  unsigned ray = 0;
+  d3 o = d3_make(0, 0, 0), d = d3_make(0, 0, 1);
+  RayF rf;
+  rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
+  HitRec best;
+  best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
+  int2 stack_mem[RTB_STACK_SIZE - WF_SMEM_STACK];
+  WalkStack<WF_SMEM_STACK> stack = { &s_stack[0][threadIdx.x], stack_mem, 128 };
+  int sp = 0;
+  int cur = RTB_REF_NONE;
+  unsigned node_visits = 0, prim_tests = 0;
+
+  while (true)
+  {
+    /* ---- refill idle lanes ---- */
+    unsigned bidle = __ballot_sync(WF_FULL, !active);
+    while (bidle != 0u && !pool_empty)
+    {
+      if (next >= end)
+      {
+        unsigned base = 0;
+        if (lane == 0)
+          base = atomicAdd(fetch_ctr, batch);
+        base = __shfl_sync(WF_FULL, base, 0);
+        if (base >= n)
+        {
+          pool_empty = true;
+          break;
+        }
+        next = base;
+        end = min(base + batch, n);
+      }
+      const unsigned mine = next + (unsigned)__popc(bidle & ((1u << lane) - 1u));
+      if (!active && mine < end)
+      {
+        ray = mine;
+        const double2 a = q.o_xy[mine], b = q.oz_dx[mine], c = q.d_yz[mine];
+        o = d3_make(a.x, a.y, b.x);
+        d = d3_make(b.y, c.x, c.y);
+        best = unpack_hit(q.hit[mine]);
+        rayf_basic(o, d, rf);
+        if (rayf_walk_setup(sv, o, d, best, rf))
+        {
+          sp = 0;
+          cur = sv.root_ref;
+          active = cur != RTB_REF_NONE;
+        }
+        /* else: the seeded hit record is already final, the lane stays idle */
+      }
+      next = min(next + (unsigned)__popc(bidle), end);
+      /* lanes the batch could not serve try the next batch; a lane whose ray needed no walk
+       * (the seeded hit record is final) is refilled on the next trip of the outer loop */
+      bidle = __ballot_sync(WF_FULL, !active && mine >= end);
+    }
+    if (__all_sync(WF_FULL, !active))
+    {
+      if (pool_empty)
+        break;
+      continue;
+    }
+
+    /* ---- walk until enough lanes are idle again ---- */
+    while (true)
+    {
+      while (cur >= 0 && cur != RTB_REF_NONE)
+      {
+        if (STATS) node_visits++;
+        int nxt = node_step(sv, rf, cur, stack, sp);
+        cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+      }
+      if (cur != RTB_REF_NONE)
+      {
+        const int code = ~cur;
+        const int first = code >> 3, count = (code & 7) + 1;
+        for (int k = 0; k < count; k++)
+          test_prim(load_prim(sv.prims, first + k), first + k, o, d, best);
+        if (STATS) prim_tests += (unsigned)count;
+        rayf_update_tmax(rf, best);
+        cur = stack_pop(rf, stack, sp);
+      }
+      if (active && cur == RTB_REF_NONE)
+      {
+        q.hit[ray] = pack_hit(best);
+        active = false;
+      }
+      const unsigned bact = __ballot_sync(WF_FULL, active);
+      if (bact == 0u)
+        break;
+      if (!pool_empty && 32 - __popc(bact) >= refill_idle)
+        break;
+    }
+  }
+
+  if (STATS)
+    wf_add_counters(totals, lane, 0ull, 0ull, prim_tests, node_visits, 0ull);
+}
+
+/* ---- shading of a whole queue ------------------------------------------------------------------
+ * Thread i handles ray i: the body of trace_path after intersect() (path_shade), then, if the
+ * path goes on, the oversized-list test of the NEXT ray and a warp-aggregated append. */
+__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ RenderArgs A, int wave, int depth, WfQueue qin,
+                                                  const unsigned *__restrict__ n_in, WfQueue qout, unsigned *n_out,
+                                                  float4 *__restrict__ planes)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned n = *n_in;
+  const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned n_px = (unsigned)(A.width * A.height);
+  PathCounters pc = { 0u, 0u };
+  unsigned exact = 0;
+
+  for (unsigned base = gwarp * 32u; base < n; base += n_warps * 32u)
+  {
+    const unsigned i = base + (unsigned)lane;
+    PathState st;
+    st.o = d3_make(0, 0, 0);
+    st.d = d3_make(0, 0, 1);
+    st.tr = st.tg = st.tb = 0.0f;
+    st.depth = depth;
+    st.alive = false;
+    unsigned pid = 0;
+    HitRec seed;
+    seed.t = DBL_MAX; seed.gid = 0x7FFFFFFF; seed.slot = 0;
+    if (i < n)
+    {
+      const uint4 p = qin.path[i];
+      const double2 a = qin.o_xy[i], b = qin.oz_dx[i], c = qin.d_yz[i];
+      const HitRec best = unpack_hit(qin.hit[i]);
+      pid = p.x;
+      st.o = d3_make(a.x, a.y, b.x);
+      st.d = d3_make(b.y, c.x, c.y);
+      st.tr = __uint_as_float(p.y); st.tg = __uint_as_float(p.z); st.tb = __uint_as_float(p.w);
+      st.alive = true;
+      const unsigned plane = pid / n_px;
+      const unsigned pixel = pid - plane * n_px;
+      const unsigned sample = (unsigned)(A.s_begin + (int)plane * A.chunk + wave);
+      float4 acc = planes[pid];
+      const float4 before = acc;
+      pc.rays++;
+      pc.rays_hit++;
+      path_shade(A, st, best, pixel, sample, acc.x, acc.y, acc.z, pc, nullptr);
+      if (__float_as_uint(acc.x) != __float_as_uint(before.x) || __float_as_uint(acc.y) != __float_as_uint(before.y) ||
+          __float_as_uint(acc.z) != __float_as_uint(before.z))
+        planes[pid] = acc;
+      if (st.alive)
+        ray_seed_hit(A.sv, st.o, st.d, seed, exact);
+    }
+    wf_enqueue(qout, n_out, st.alive, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed);
+  }
+  wf_add_counters(A.counters, lane, pc.rays, pc.rays_hit, exact, 0ull, 0ull);
+}
+
+/* out[pixel][c] = sum over planes, in plane order (deterministic; same order as k_sum_planes) */
+__global__ void k_wf_sum_planes(const float4 *__restrict__ planes, int n_planes, unsigned n_px, float *__restrict__ out)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px)
+    return;
+  float r = 0.0f, g = 0.0f, b = 0.0f;
+  for (int k = 0; k < n_planes; k++)
+  {
+    const float4 v = planes[(size_t)k * n_px + i];
+    r += v.x; g += v.y; b += v.z;
+  }
+  out[3 * (size_t)i + 0] = r;
+  out[3 * (size_t)i + 1] = g;
+  out[3 * (size_t)i + 2] = b;
+}
+
+/* ---- host ---------------------------------------------------------------------------------- */
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, float *d_accum, cudaStream_t stream,
+              bool stats, unsigned long long &launches)
+{
+  const int spp = A.s_end - A.s_begin;
+  const size_t n_px = (size_t)A.width * A.height;
+  const size_t slots = n_px * (size_t)A.splits;
+  if (slots >= (1ull << 31))
+  {
+    rtb_set_error("wavefront: width*height*planes must stay below 2^31");
+    return RTB_EINVAL;
+  }
+  const int n_bounces = A.max_depth + 1;
+
+  /* one allocation: 2 queues x 5 arrays of 16 B, the planes, the per-wave counters */
+  const size_t arr = align_up(slots * 16, 256);
+  const size_t ctr_bytes = align_up(sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), 256);
+  const size_t need = arr * 11 + ctr_bytes;
+  if (scene->wf_bytes < need)
+  {
+    if (scene->d_wf)
+      RTB_CUDA(cudaFreeAsync(scene->d_wf, stream));
+    scene->d_wf = nullptr;
+    scene->wf_bytes = 0;
+    RTB_CUDA(cudaMallocAsync(&scene->d_wf, need, stream));
+    scene->wf_bytes = need;
+  }
+  char *p = static_cast<char *>(scene->d_wf);
+  WfQueue q[2];
+  for (int k = 0; k < 2; k++)
+  {
+    q[k].o_xy = reinterpret_cast<double2 *>(p); p += arr;
+    q[k].oz_dx = reinterpret_cast<double2 *>(p); p += arr;
+    q[k].d_yz = reinterpret_cast<double2 *>(p); p += arr;
+    q[k].path = reinterpret_cast<uint4 *>(p); p += arr;
+    q[k].hit = reinterpret_cast<uint4 *>(p); p += arr;
+  }
+  float4 *planes = reinterpret_cast<float4 *>(p); p += arr;
+  unsigned *counts = reinterpret_cast<unsigned *>(p);            /* [n_bounces + 2] queue lengths */
+  unsigned *fetch = counts + (n_bounces + 2);                    /* [n_bounces + 2] trace fetch cursors */
+
+  RTB_CUDA(cudaMemsetAsync(planes, 0, slots * 16, stream));
+
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device);
+  const int refill_idle = (desc->reserved > 0 && desc->reserved <= 32) ? desc->reserved : 8;
+  const int trace_blocks = sm_count * WF_TRACE_BLOCKS_PER_SM;
+  const int shade_blocks = sm_count * 16;
+  const long long gen_warps = (long long)A.n_tiles * A.splits;
+  const int gen_blocks = (int)((gen_warps * 32 + 127) / 128);
+
+  for (int wave = 0; wave < A.chunk; wave++)
+  {
+    RTB_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), stream));
+    k_wf_generate<<<gen_blocks, 128, 0, stream>>>(A, wave, q[0], &counts[0]);
+    launches++;
+    for (int b = 0; b < n_bounces; b++)
+    {
+      const WfQueue &qi = q[b & 1], &qo = q[(b + 1) & 1];
+      if (stats)
+        k_wf_trace<true><<<trace_blocks, 128, 0, stream>>>(A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle);
+      else
+        k_wf_trace<false><<<trace_blocks, 128, 0, stream>>>(A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle);
+      k_wf_shade<<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes);
+      launches += 2;
+    }
+    RTB_CUDA(cudaGetLastError());
+  }
+  (void)spp;
+  k_wf_sum_planes<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(planes, A.splits, (unsigned)n_px, d_accum);
+  RTB_CUDA(cudaGetLastError());
+  launches++;
+  return RTB_OK;
+}

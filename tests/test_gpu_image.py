@@ -73,10 +73,11 @@ def test_golden_hits_on_device(gpu_api):
             np.testing.assert_allclose(got["uvs"], g["uvs"], rtol=0, atol=1e-15)  # atan2: libm vs CUDA
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6])
 def test_kernel_variants_agree(gpu_api, kernel):
-    """megakernel, warp-scheduled state machine and the FP32 pre-test variants compute the
-    same per-pixel sums (same lanes, same Philox streams, same exact tests)"""
+    """megakernel, warp-scheduled state machine, the FP32 pre-test variants and the wavefront
+    kernels compute the same per-pixel sums (same Philox streams, same exact tests, same
+    order of additions)"""
     W, H, SPP = 96, 54, 8
     objs = gpu_api.scene_sphere_field(400, W, H, mix=(0.3, 0.3, 0.3))
     cam = gpu_api.init_camera(W, H)
@@ -85,6 +86,37 @@ def test_kernel_variants_agree(gpu_api, kernel):
         _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 0, SPP, max_depth=8, kernel=kernel), want_accum=True)
     assert np.array_equal(acc, base)
     assert c0.rays == c1.rays and c0.paths == c1.paths
+
+
+@pytest.mark.parametrize("spp,planes", [(7, 3), (6, 1), (5, 5), (9, 2)])
+def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
+    """wavefront (ray queues + persistent trace kernel) vs megakernel on a mesh + spheres scene,
+    including ragged plane/wave combinations: bit-identical sums and equal counters"""
+    W, H = 80, 46  # not a multiple of the 8x4 tile
+    verts = gpu_api.heightfield_mesh(40, 20 * W / H * 0.98)
+    holder = gpu_api.mesh_room(verts, W, H)
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(holder) as sc:
+        _, base, c0 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=4, planes=planes), want_accum=True)
+        _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes), want_accum=True)
+        _, acc2, c2 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=1), want_accum=True)
+    assert np.array_equal(acc, base) and np.array_equal(acc2, base)
+    assert c0.rays == c1.rays == c2.rays and c0.paths == c1.paths == W * H * spp
+    assert c0.rays_intersected == c1.rays_intersected
+    assert c1.node_visits == c0.node_visits and c1.prim_tests == c0.prim_tests
+
+
+def test_wavefront_depth_zero_and_empty(gpu_api):
+    """max_depth 0 (one vertex per path) and an empty sample range"""
+    W, H = 64, 36
+    objs = gpu_api.scene_default(W, H)
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        _, a0, c0 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=0, kernel=4), want_accum=True)
+        _, a1, c1 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=0, kernel=6), want_accum=True)
+        _, e, ce = sc.render(cam, gpu_api.make_desc(W, H, 5, 5, kernel=6), want_accum=True)
+    assert np.array_equal(a0, a1) and c0.rays == c1.rays
+    assert not e.any() and ce.rays == 0
 
 
 def test_full_size_properties(gpu_api):
