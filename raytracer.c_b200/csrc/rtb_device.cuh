@@ -343,15 +343,25 @@ struct WalkStack
   }
 };
 
+/* 256-bit read-only global load (pointer must be 32-byte aligned) */
+__device__ __forceinline__ void ld256_nc(const float4 *p, float4 &a, float4 &b)
+{
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 /* One inner node: tests both children, returns the reference to continue with
  * (RTB_REF_NONE if neither is hit) and pushes the farther one. */
 template <int SD>
 __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
 {
-  const float4 n0 = __ldg(sv.nodes + 4 * cur + 0);
-  const float4 n1 = __ldg(sv.nodes + 4 * cur + 1);
-  const float4 n2 = __ldg(sv.nodes + 4 * cur + 2);
-  const float4 n3 = __ldg(sv.nodes + 4 * cur + 3);
+  /* 64-byte node = two 256-bit loads (LDG.E.256, new on sm_100): half the L1 wavefronts of
+   * four 128-bit loads -- the L1 data pipe was 60 % busy with node fetches
+   * (profiles/r1_wf_trace_ncu.md) */
+  float4 n0, n1, n2, n3;
+  ld256_nc(sv.nodes + 4 * cur, n0, n1);
+  ld256_nc(sv.nodes + 4 * cur + 2, n2, n3);
 
   float c0lx = fmaf(n0.x, rf.idx, -rf.oodx), c0hx = fmaf(n0.y, rf.idx, -rf.oodx);
   float c0ly = fmaf(n0.z, rf.idy, -rf.oody), c0hy = fmaf(n0.w, rf.idy, -rf.oody);

@@ -158,13 +158,31 @@ __global__ void __launch_bounds__(128) k_wf_generate(const __grid_constant__ Ren
  * keeps its lanes supplied from the batch: whenever `refill_idle` or more lanes have no ray,
  * the walk is interrupted and the idle lanes load the next rays.  The walk itself is the
  * while-while loop of closest_hit_ww (inner nodes until every lane has reached a leaf, then
- * the exact FP64 leaf tests together). */
-template <bool STATS>
-__global__ void __launch_bounds__(128, WF_TRACE_BLOCKS_PER_SM)
-k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
-           unsigned long long *totals, int refill_idle)
+ * the exact FP64 leaf tests together).
+ * V (variant bits): 1 = the double-precision ray is NOT kept in registers during the walk but
+ * re-read from the queue at every leaf (fewer registers -> more warps per SM);
+ * 2 = streaming (evict-first) loads/stores for queue data; 4 = whole traversal stack in local
+ * memory (no shared-memory top); 8 = postponed leaf: a lane that reaches a leaf stashes it and
+ * keeps walking (speculatively) until it meets a second leaf, so more lanes stay in the node phase. */
+template <int V> struct WfTraceCfg { static constexpr int blocks = (V & 1) ? 10 : 8; static constexpr int sd = (V & 4) ? 0 : WF_SMEM_STACK; };
+
+__device__ __forceinline__ double2 wf_ld(const double2 *p, bool stream)
 {
-  __shared__ int2 s_stack[WF_SMEM_STACK][128];
+  return stream ? __ldcs(p) : *p;
+}
+__device__ __forceinline__ uint4 wf_ld(const uint4 *p, bool stream)
+{
+  return stream ? __ldcs(p) : *p;
+}
+
+template <bool STATS, int V>
+__global__ void __launch_bounds__(128, WfTraceCfg<V>::blocks)
+k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
+           unsigned long long *totals, int refill_idle, int node_exit)
+{
+  constexpr bool RELOAD = (V & 1) != 0, STREAM = (V & 2) != 0, STASH = (V & 8) != 0;
+  constexpr int SD = WfTraceCfg<V>::sd;
+  __shared__ int2 s_stack[SD > 0 ? SD : 1][128];
   const int lane = threadIdx.x & 31;
   const unsigned n = *n_ptr;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -182,10 +200,11 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
   rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
   HitRec best;
   best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
-  int2 stack_mem[RTB_STACK_SIZE - WF_SMEM_STACK];
-  WalkStack<WF_SMEM_STACK> stack = { &s_stack[0][threadIdx.x], stack_mem, 128 };
+  int2 stack_mem[RTB_STACK_SIZE - SD];
+  WalkStack<SD> stack = { &s_stack[0][threadIdx.x], stack_mem, 128 };
   int sp = 0;
   int cur = RTB_REF_NONE;
+  int stash = RTB_REF_NONE; /* STASH: a leaf waiting for the next leaf phase */
   unsigned node_visits = 0, prim_tests = 0;
 
   while (true)
@@ -212,16 +231,20 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
       if (!active && mine < end)
       {
         ray = mine;
-        const double2 a = q.o_xy[mine], b = q.oz_dx[mine], c = q.d_yz[mine];
-        o = d3_make(a.x, a.y, b.x);
-        d = d3_make(b.y, c.x, c.y);
-        best = unpack_hit(q.hit[mine]);
-        rayf_basic(o, d, rf);
-        if (rayf_walk_setup(sv, o, d, best, rf))
+        const double2 a = wf_ld(q.o_xy + mine, STREAM), b = wf_ld(q.oz_dx + mine, STREAM), c = wf_ld(q.d_yz + mine, STREAM);
+        d3 o_ = d3_make(a.x, a.y, b.x), d_ = d3_make(b.y, c.x, c.y);
+        best = unpack_hit(wf_ld(q.hit + mine, STREAM));
+        rayf_basic(o_, d_, rf);
+        if (rayf_walk_setup(sv, o_, d_, best, rf))
         {
           sp = 0;
           cur = sv.root_ref;
           active = cur != RTB_REF_NONE;
+        }
+        if (!RELOAD)
+        {
+          o = o_;
+          d = d_;
         }
         /* else: the seeded hit record is already final, the lane stays idle */
       }
@@ -240,14 +263,75 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
     /* ---- walk until enough lanes are idle again ---- */
     while (true)
     {
-      while (cur >= 0 && cur != RTB_REF_NONE)
+      if (node_exit <= 0)
       {
-        if (STATS) node_visits++;
-        int nxt = node_step(sv, rf, cur, stack, sp);
-        cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+        while (cur >= 0 && cur != RTB_REF_NONE)
+        {
+          if (STATS) node_visits++;
+          int nxt = node_step(sv, rf, cur, stack, sp);
+          cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+        }
       }
-      if (cur != RTB_REF_NONE)
+      else
       {
+        /* leave the node phase as soon as fewer than node_exit lanes are still at inner nodes */
+        while (true)
+        {
+          if (STASH && cur < 0 && stash == RTB_REF_NONE)
+          {
+            stash = cur;
+            cur = stack_pop(rf, stack, sp);
+          }
+          const bool at_node = cur >= 0 && cur != RTB_REF_NONE;
+          const unsigned bnode = __ballot_sync(WF_FULL, at_node);
+          if (bnode == 0u)
+            break;
+          if (at_node)
+          {
+            if (STATS) node_visits++;
+            int nxt = node_step(sv, rf, cur, stack, sp);
+            cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+          }
+          if (__popc(bnode) < node_exit)
+            break;
+        }
+      }
+      if (STASH)
+      {
+        /* the leaf to test now: the stashed one first (it was met first) */
+        if (stash == RTB_REF_NONE && cur < 0)
+        {
+          stash = cur;
+          cur = stack_pop(rf, stack, sp);
+        }
+        if (stash != RTB_REF_NONE)
+        {
+          if (RELOAD)
+          {
+            const double2 a = q.o_xy[ray], b = q.oz_dx[ray], c = q.d_yz[ray];
+            o = d3_make(a.x, a.y, b.x);
+            d = d3_make(b.y, c.x, c.y);
+          }
+          const int code = ~stash;
+          const int first = code >> 3, count = (code & 7) + 1;
+          for (int k = 0; k < count; k++)
+            test_prim(load_prim(sv.prims, first + k), first + k, o, d, best);
+          if (STATS) prim_tests += (unsigned)count;
+          rayf_update_tmax(rf, best);
+          stash = RTB_REF_NONE;
+          /* an inner node popped speculatively may be out of range now: it is simply visited
+           * (its children fail the slab test); a speculatively popped LEAF is kept */
+        }
+      }
+      else
+      if (cur < 0)
+      {
+        if (RELOAD)
+        {
+          const double2 a = q.o_xy[ray], b = q.oz_dx[ray], c = q.d_yz[ray];
+          o = d3_make(a.x, a.y, b.x);
+          d = d3_make(b.y, c.x, c.y);
+        }
         const int code = ~cur;
         const int first = code >> 3, count = (code & 7) + 1;
         for (int k = 0; k < count; k++)
@@ -256,9 +340,12 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         rayf_update_tmax(rf, best);
         cur = stack_pop(rf, stack, sp);
       }
-      if (active && cur == RTB_REF_NONE)
+      if (active && cur == RTB_REF_NONE && stash == RTB_REF_NONE)
       {
-        q.hit[ray] = pack_hit(best);
+        if (STREAM)
+          __stcs(q.hit + ray, pack_hit(best));
+        else
+          q.hit[ray] = pack_hit(best);
         active = false;
       }
       const unsigned bact = __ballot_sync(WF_FULL, active);
@@ -271,6 +358,18 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
 
   if (STATS)
     wf_add_counters(totals, lane, 0ull, 0ull, prim_tests, node_visits, 0ull);
+}
+
+template <int V>
+static void launch_trace(bool stats, int blocks_per_sm_unused, int sm_count, cudaStream_t stream, const SceneView &sv,
+                         const WfQueue &q, const unsigned *n_ptr, unsigned *fetch, unsigned long long *totals,
+                         int refill_idle, int node_exit)
+{
+  const int blocks = sm_count * WfTraceCfg<V>::blocks;
+  if (stats)
+    k_wf_trace<true, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit);
+  else
+    k_wf_trace<false, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit);
 }
 
 /* ---- shading of a whole queue ------------------------------------------------------------------
@@ -394,8 +493,19 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
 
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device);
-  const int refill_idle = (desc->reserved > 0 && desc->reserved <= 32) ? desc->reserved : 8;
-  const int trace_blocks = sm_count * WF_TRACE_BLOCKS_PER_SM;
+  /* tuning word (desc->reserved): bits 0-7 refill threshold, 8-15 node-phase exit threshold,
+   * 16-23 trace kernel variant */
+  const int refill_idle = ((desc->reserved & 0xFF) > 0 && (desc->reserved & 0xFF) <= 32) ? (desc->reserved & 0xFF) : 8;
+  int node_exit = (desc->reserved >> 8) & 0xFF;
+  int variant = (desc->reserved >> 16) & 0xFF;
+  if (desc->reserved == 0)
+  {
+    /* measured defaults (profiles/r1_wf_tuning.md) */
+    node_exit = 16;
+    variant = 2;
+  }
+  if (node_exit == 0xFF)
+    node_exit = 0; /* pure while-while */
   const int shade_blocks = sm_count * 16;
   const long long gen_warps = (long long)A.n_tiles * A.splits;
   const int gen_blocks = (int)((gen_warps * 32 + 127) / 128);
@@ -408,10 +518,18 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     for (int b = 0; b < n_bounces; b++)
     {
       const WfQueue &qi = q[b & 1], &qo = q[(b + 1) & 1];
-      if (stats)
-        k_wf_trace<true><<<trace_blocks, 128, 0, stream>>>(A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle);
-      else
-        k_wf_trace<false><<<trace_blocks, 128, 0, stream>>>(A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle);
+      switch (variant)
+      {
+      case 2: launch_trace<2>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 4: launch_trace<4>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 6: launch_trace<6>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 8: launch_trace<8>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 10: launch_trace<10>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 12: launch_trace<12>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 14: launch_trace<14>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 1: launch_trace<1>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      default: launch_trace<0>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      }
       k_wf_shade<<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes);
       launches += 2;
     }
