@@ -220,7 +220,7 @@ def render(objects, camera, width, height, samples):
 
 # ---- the C ABI ----------------------------------------------------------------------------
 
-def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0):
+def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0):
     d = abi.RtbRenderDesc()
     d.width, d.height = width, height
     d.sample_begin, d.sample_end = sample_begin, sample_end
@@ -230,6 +230,7 @@ def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCE
     d.kernel = kernel
     d.reserved = tune
     d.planes = planes
+    d.reserved2 = tune2
     return d
 
 

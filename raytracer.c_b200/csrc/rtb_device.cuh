@@ -390,6 +390,112 @@ __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, in
   return RTB_REF_NONE;
 }
 
+/* One BVH4 node: tests up to four children, continues with the nearest one hit and pushes the
+ * others far-to-near (so the nearer is popped first). */
+__device__ __forceinline__ void cswap(float &da, int &ra, float &db, int &rb)
+{
+  const bool s = db < da;
+  const float dt = s ? db : da, du = s ? da : db;
+  const int rt = s ? rb : ra, ru = s ? ra : rb;
+  da = dt; db = du; ra = rt; rb = ru;
+}
+
+template <int SD>
+__device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+{
+  const float4 *np = sv.nodes4 + 8 * (size_t)cur;
+  float4 lox, hix, loy, hiy, loz, hiz, rr, spare;
+  ld256_nc(np + 0, lox, hix);
+  ld256_nc(np + 2, loy, hiy);
+  ld256_nc(np + 4, loz, hiz);
+  ld256_nc(np + 6, rr, spare);
+  const float INF = 3.0e38f;
+  float dist[4];
+  int ref[4] = { __float_as_int(rr.x), __float_as_int(rr.y), __float_as_int(rr.z), __float_as_int(rr.w) };
+  const float lx[4] = { lox.x, lox.y, lox.z, lox.w }, hx[4] = { hix.x, hix.y, hix.z, hix.w };
+  const float ly[4] = { loy.x, loy.y, loy.z, loy.w }, hy[4] = { hiy.x, hiy.y, hiy.z, hiy.w };
+  const float lz[4] = { loz.x, loz.y, loz.z, loz.w }, hz[4] = { hiz.x, hiz.y, hiz.z, hiz.w };
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+  {
+    const float ax = fmaf(lx[k], rf.idx, -rf.oodx), bx = fmaf(hx[k], rf.idx, -rf.oodx);
+    const float ay = fmaf(ly[k], rf.idy, -rf.oody), by = fmaf(hy[k], rf.idy, -rf.oody);
+    const float az = fmaf(lz[k], rf.idz, -rf.oodz), bz = fmaf(hz[k], rf.idz, -rf.oodz);
+    const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), rf.tmax));
+    const bool hit = (tmin <= tmax * RTB_WIDEN) && ref[k] != RTB_REF_NONE;
+    dist[k] = hit ? tmin : INF;
+  }
+  /* sorting network for 4 keys */
+  cswap(dist[0], ref[0], dist[1], ref[1]);
+  cswap(dist[2], ref[2], dist[3], ref[3]);
+  cswap(dist[0], ref[0], dist[2], ref[2]);
+  cswap(dist[1], ref[1], dist[3], ref[3]);
+  cswap(dist[1], ref[1], dist[2], ref[2]);
+  if (dist[0] >= INF)
+    return RTB_REF_NONE;
+  if (dist[3] < INF) { stack.put(sp, make_int2(ref[3], __float_as_int(dist[3]))); sp++; }
+  if (dist[2] < INF) { stack.put(sp, make_int2(ref[2], __float_as_int(dist[2]))); sp++; }
+  if (dist[1] < INF) { stack.put(sp, make_int2(ref[1], __float_as_int(dist[1]))); sp++; }
+  return ref[0];
+}
+
+/* One compressed BVH4 node (Bvh4QNode): slab distances straight from the quantised planes,
+ * t = q * (2^e / d) + (origin - o) / d */
+__device__ __forceinline__ float qbyte(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
+
+template <int SD>
+__device__ __forceinline__ int node_step4q(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+{
+  const float4 *np = sv.nodes4q + 4 * (size_t)cur;
+  float4 w0, w1, w2, w3;
+  ld256_nc(np + 0, w0, w1);
+  ld256_nc(np + 2, w2, w3);
+  const unsigned eb = __float_as_uint(w0.w);
+  const float sx = __uint_as_float((eb & 0xFFu) << 23) * rf.idx;
+  const float sy = __uint_as_float(((eb >> 8) & 0xFFu) << 23) * rf.idy;
+  const float sz = __uint_as_float(((eb >> 16) & 0xFFu) << 23) * rf.idz;
+  const float bx = fmaf(w0.x, rf.idx, -rf.oodx), by = fmaf(w0.y, rf.idy, -rf.oody), bz = fmaf(w0.z, rf.idz, -rf.oodz);
+  const unsigned qlx = __float_as_uint(w2.x), qly = __float_as_uint(w2.y), qlz = __float_as_uint(w2.z);
+  const unsigned qhx = __float_as_uint(w2.w), qhy = __float_as_uint(w3.x), qhz = __float_as_uint(w3.y);
+  const float INF = 3.0e38f;
+  float dist[4];
+  int ref[4] = { __float_as_int(w1.x), __float_as_int(w1.y), __float_as_int(w1.z), __float_as_int(w1.w) };
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+  {
+    const float ax = fmaf(qbyte(qlx, k), sx, bx), cx = fmaf(qbyte(qhx, k), sx, bx);
+    const float ay = fmaf(qbyte(qly, k), sy, by), cy = fmaf(qbyte(qhy, k), sy, by);
+    const float az = fmaf(qbyte(qlz, k), sz, bz), cz = fmaf(qbyte(qhz, k), sz, bz);
+    const float tmin = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), rf.tmax));
+    const bool hit = (tmin <= tmax * RTB_WIDEN) && ref[k] != RTB_REF_NONE;
+    dist[k] = hit ? tmin : INF;
+  }
+  cswap(dist[0], ref[0], dist[1], ref[1]);
+  cswap(dist[2], ref[2], dist[3], ref[3]);
+  cswap(dist[0], ref[0], dist[2], ref[2]);
+  cswap(dist[1], ref[1], dist[3], ref[3]);
+  cswap(dist[1], ref[1], dist[2], ref[2]);
+  if (dist[0] >= INF)
+    return RTB_REF_NONE;
+  if (dist[3] < INF) { stack.put(sp, make_int2(ref[3], __float_as_int(dist[3]))); sp++; }
+  if (dist[2] < INF) { stack.put(sp, make_int2(ref[2], __float_as_int(dist[2]))); sp++; }
+  if (dist[1] < INF) { stack.put(sp, make_int2(ref[1], __float_as_int(dist[1]))); sp++; }
+  return ref[0];
+}
+
+/* WIDE: 0 = BvhNode (two children, 64 B), 1 = Bvh4Node (128 B), 2 = Bvh4QNode (compressed, 64 B) */
+template <int SD, int WIDE>
+__device__ __forceinline__ int node_step_w(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+{
+  if (WIDE == 2)
+    return node_step4q(sv, rf, cur, stack, sp);
+  if (WIDE == 1)
+    return node_step4(sv, rf, cur, stack, sp);
+  return node_step(sv, rf, cur, stack, sp);
+}
+
 /* pop the next subtree that can still contain a nearer hit; RTB_REF_NONE when done */
 template <int SD>
 __device__ __forceinline__ int stack_pop(const RayF &rf, const WalkStack<SD> &stack, int &sp)
@@ -524,7 +630,7 @@ __device__ __forceinline__ void big_list_select_test(const SceneView &sv, const 
  * (profiles/r1_c3_megakernel_ncu.md).  The oversized list is handled "select, then test":
  * an FP32 lower bound per sphere picks the most promising one, which is tested exactly by
  * all lanes at once; the few others whose bound still beats the result follow. */
-template <bool STATS, int SD>
+template <bool STATS, int SD, int WIDE = 0>
 __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best,
                                                TraceStats &st, int2 *smem_column, int smem_stride)
 {
@@ -548,7 +654,7 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
       while (cur >= 0 && cur != RTB_REF_NONE)
       {
         if (STATS) st.node_visits++;
-        int nxt = node_step(sv, rf, cur, stack, sp);
+        int nxt = node_step_w<SD, WIDE>(sv, rf, cur, stack, sp);
         cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
       }
       if (cur == RTB_REF_NONE)

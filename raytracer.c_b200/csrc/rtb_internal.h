@@ -52,6 +52,25 @@ struct PrimRec { float4 a, b, c; };
  * ref >= 0: inner node index; ref < 0: leaf, ~ref = (first << 3) | (count - 1), `first`
  * indexing the BVH-ordered primitive array. */
 struct BvhNode { float4 n0, n1, n2, n3; };
+
+/* BVH4 node, 128 bytes (four 256-bit loads): the BVH2 collapsed by two levels -- every inner
+ * node at even depth absorbs its inner children.  Half the dependent fetches per ray.
+ *   q0 = lo.x of children 0..3, q1 = hi.x, q2 = lo.y, q3 = hi.y, q4 = lo.z, q5 = hi.z
+ *   q6 = child references as int bits (same encoding as BvhNode; RTB_REF_NONE = empty slot)
+ *   q7 = unused
+ * Indexed like BvhNode by the Karras index of the inner node it was made from. */
+struct Bvh4Node { float4 q[8]; };
+
+/* Compressed BVH4 node, 64 bytes (two 256-bit loads): child boxes quantised to 8 bits per
+ * coordinate on a per-node grid (origin + q * 2^e per axis, after Ylitie et al. 2017); lo is
+ * rounded down and hi up, so a decoded box always contains the padded float box.
+ *   w0 = {origin.x, origin.y, origin.z, ex | ey << 8 | ez << 16}   e = IEEE-754 exponent byte of the cell size
+ *   w1 = child references (int bits, RTB_REF_NONE = empty slot)
+ *   w2 = {qlo.x[0..3], qlo.y[0..3], qlo.z[0..3], qhi.x[0..3]}      one byte per child
+ *   w3 = {qhi.y[0..3], qhi.z[0..3], -, -}
+ * The L1 data pipe is the bound of the walk (one wavefront per 32-byte sector a lane touches):
+ * this node costs 2 wavefronts per visit instead of 4 (Bvh4Node) or 2 x 2 (two BvhNode). */
+struct Bvh4QNode { float4 w[4]; };
 #define RTB_LEAF_MAX 4
 #define RTB_STACK_SIZE 64
 #define RTB_REF_NONE 0x7FFFFFFF
@@ -59,6 +78,8 @@ struct BvhNode { float4 n0, n1, n2, n3; };
 struct SceneView
 {
   const float4 *nodes; /* 4 float4 per node */
+  const float4 *nodes4; /* 8 float4 per BVH4 node */
+  const float4 *nodes4q; /* 4 float4 per compressed BVH4 node */
   const float4 *prims; /* 3 float4 per BVH primitive, BVH order */
   const float4 *big;   /* 3 float4 per oversized primitive (tested for every ray) */
   const float4 *mats;  /* 2 float4 per object */
@@ -72,6 +93,7 @@ struct rtb_scene
   int device = 0;
   SceneView view{};
   /* owned device allocations */
+  float4 *d_nodes4 = nullptr, *d_nodes4q = nullptr;
   float4 *d_nodes = nullptr, *d_prims = nullptr, *d_big = nullptr, *d_mats = nullptr;
   float2 *d_tex = nullptr;
   float *d_scratch = nullptr; /* split planes */

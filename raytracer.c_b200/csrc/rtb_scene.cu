@@ -394,6 +394,124 @@ __global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restri
   atomicAdd(emitted, 1);
 }
 
+/* BVH4: one 128-byte node per inner node at EVEN depth whose subtree holds more than leaf_max
+ * primitives; its inner children (odd depth) are absorbed, so it has 2..4 children */
+__global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restrict__ box_lo,
+                        const float4 *__restrict__ box_hi, int n, const int2 *__restrict__ children,
+                        const int *__restrict__ range_first, const float4 *__restrict__ node_lo,
+                        const float4 *__restrict__ node_hi, const int *__restrict__ parent_inner,
+                        const BuildParams *__restrict__ bp, float4 *__restrict__ out_nodes,
+                        float4 *__restrict__ out_nodes_q, int *__restrict__ emitted, int leaf_max)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  if (__float_as_int(node_lo[i].w) <= leaf_max)
+    return;
+  int depth = 0;
+  for (int p = parent_inner[i]; p >= 0; p = parent_inner[p])
+    depth++;
+  if (depth & 1)
+    return;
+  const float pad = bp->pad;
+  float lo[4][3], hi[4][3];
+  int ref[4];
+  int m = 0;
+  auto add = [&](int c, bool may_be_inner) -> bool {
+    float4 a, b;
+    int r;
+    if (c < 0)
+    {
+      unsigned p = vals[~c];
+      a = box_lo[p]; b = box_hi[p];
+      r = leaf_ref(~c, 1);
+    }
+    else
+    {
+      a = node_lo[c]; b = node_hi[c];
+      int cc = __float_as_int(a.w);
+      if (cc <= leaf_max)
+        r = leaf_ref(range_first[c], cc);
+      else if (may_be_inner)
+        r = c;
+      else
+        return false; /* inner child of the node itself: absorb */
+    }
+    lo[m][0] = a.x - pad; lo[m][1] = a.y - pad; lo[m][2] = a.z - pad;
+    hi[m][0] = b.x + pad; hi[m][1] = b.y + pad; hi[m][2] = b.z + pad;
+    ref[m] = r;
+    m++;
+    return true;
+  };
+  const int2 ch = children[i];
+  const int c2[2] = { ch.x, ch.y };
+  for (int k = 0; k < 2; k++)
+    if (!add(c2[k], false))
+    {
+      const int2 g = children[c2[k]];
+      add(g.x, true);
+      add(g.y, true);
+    }
+  for (; m < 4; m++)
+  {
+    for (int a = 0; a < 3; a++) { lo[m][a] = 0.0f; hi[m][a] = 0.0f; }
+    ref[m] = RTB_REF_NONE;
+  }
+  float4 *o = out_nodes + 8 * (size_t)i;
+  o[0] = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+  o[1] = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+  o[2] = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+  o[3] = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+  o[4] = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+  o[5] = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+  o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+  o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+
+  /* compressed copy: per-node grid origin + q * 2^e, lo rounded down, hi rounded up */
+  float org[3];
+  unsigned ebyte[3], qlo[3] = { 0u, 0u, 0u }, qhi[3] = { 0u, 0u, 0u };
+  for (int a = 0; a < 3; a++)
+  {
+    float nlo = 3.0e38f, nhi = -3.0e38f;
+    for (int k = 0; k < 4; k++)
+      if (ref[k] != RTB_REF_NONE)
+      {
+        nlo = fminf(nlo, lo[k][a]);
+        nhi = fmaxf(nhi, hi[k][a]);
+      }
+    org[a] = nlo;
+    /* smallest power of two s with 255 * s >= extent (computed in double, then checked) */
+    const double ext = (double)nhi - (double)nlo;
+    int e = 0;
+    frexp(ext / 255.0, &e); /* ext/255 = m * 2^e, m in [0.5, 1) -> 2^e >= ext/255 */
+    if (!(ext > 0.0))
+      e = -126;
+    e = max(-126, min(127, e));
+    double cell = ldexp(1.0, e);
+    while (cell * 255.0 < ext && e < 127) { e++; cell = ldexp(1.0, e); }
+    ebyte[a] = (unsigned)(e + 127);
+    for (int k = 0; k < 4; k++)
+    {
+      unsigned ql = 0u, qh = 0u;
+      if (ref[k] != RTB_REF_NONE)
+      {
+        double l = floor(((double)lo[k][a] - (double)nlo) / cell);
+        double h = ceil(((double)hi[k][a] - (double)nlo) / cell);
+        ql = (unsigned)fmin(fmax(l, 0.0), 255.0);
+        qh = (unsigned)fmin(fmax(h, 0.0), 255.0);
+      }
+      qlo[a] |= ql << (8 * k);
+      qhi[a] |= qh << (8 * k);
+    }
+  }
+  float4 *oq = out_nodes_q + 4 * (size_t)i;
+  oq[0] = make_float4(org[0], org[1], org[2], __uint_as_float(ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16)));
+  oq[1] = o[6];
+  oq[2] = make_float4(__uint_as_float(qlo[0]), __uint_as_float(qlo[1]), __uint_as_float(qlo[2]), __uint_as_float(qhi[0]));
+  oq[3] = make_float4(__uint_as_float(qhi[1]), __uint_as_float(qhi[2]), 0.0f, 0.0f);
+  atomicAdd(emitted, 1);
+}
+
 __global__ void k_reorder(const unsigned *__restrict__ vals, int n, const PrimRec *__restrict__ in,
                           PrimRec *__restrict__ out, const float2 *__restrict__ tex_in, float2 *__restrict__ tex_out)
 {
@@ -661,7 +779,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   DevBuf<unsigned long long> d_keys, d_keys_sorted;
   DevBuf<unsigned char> d_temp;
   DevBuf<int2> d_children;
-  DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc;
+  DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc, d_misc4;
   BuildParams h_bp;
   memset(&h_bp, 0, sizeof(h_bp));
   int h_misc[2] = { 0, 0 };
@@ -756,6 +874,8 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       RTB_CUDA(d_first.alloc(N - 1));
       RTB_CUDA(d_flags.alloc(N - 1));
       RTB_CUDA(d_misc.alloc(2));
+      RTB_CUDA(d_misc4.alloc(1));
+      RTB_CUDA(cudaMemsetAsync(d_misc4.p, 0, sizeof(int), 0));
       RTB_CUDA(d_node_lo.alloc(N - 1));
       RTB_CUDA(d_node_hi.alloc(N - 1));
       RTB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * (N - 1), 0));
@@ -773,12 +893,17 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
                             d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1, leaf_max);
       RTB_CUDA(cudaGetLastError());
+      RTB_CUDA(pool_alloc(&sc->d_nodes4, 8 * (N - 1)));
+      RTB_CUDA(pool_alloc(&sc->d_nodes4q, 4 * (N - 1)));
+      k_emit4<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
+                             d_node_hi.p, d_parent_inner.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, d_misc4.p, leaf_max);
+      RTB_CUDA(cudaGetLastError());
       k_reorder<<<blocks, T>>>(d_vals_sorted.p, (int)N, d_unsorted.p, reinterpret_cast<PrimRec *>(sc->d_prims),
                                want_tex ? d_tex_unsorted.p : nullptr, sc->d_tex);
       RTB_CUDA(cudaGetLastError());
       RTB_CUDA(cudaMemcpyAsync(h_misc, d_misc.p, sizeof(h_misc), cudaMemcpyDeviceToHost, 0));
       view.root_ref = 0;
-      dev_bytes += sizeof(BvhNode) * (N - 1);
+      dev_bytes += (sizeof(BvhNode) + sizeof(Bvh4Node) + sizeof(Bvh4QNode)) * (N - 1);
     }
     dev_bytes += sizeof(PrimRec) * N + (want_tex ? sizeof(float2) * 3 * N : 0);
   }
@@ -816,6 +941,8 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   }
 
   view.nodes = sc->d_nodes;
+  view.nodes4 = sc->d_nodes4;
+  view.nodes4q = sc->d_nodes4q;
   view.prims = sc->d_prims;
   view.big = sc->d_big;
   view.mats = sc->d_mats;
@@ -894,7 +1021,7 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
   cudaSetDevice(scene->device);
   /* stream-ordered: the memory goes back to the pool once work queued before this point on
    * the legacy default stream (which synchronises with every blocking stream) is done */
-  void *bufs[] = { scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_tex,
+  void *bufs[] = { scene->d_nodes4q, scene->d_nodes4, scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_tex,
                    scene->d_scratch, scene->d_counters, scene->d_wf };
   for (void *b : bufs)
     if (b)

@@ -27,6 +27,7 @@
 #include "rtb_path.cuh"
 
 #include <algorithm>
+#include <cub/cub.cuh>
 
 #define WF_FULL 0xFFFFFFFFu
 #ifndef WF_SMEM_STACK
@@ -75,9 +76,63 @@ __device__ __forceinline__ void ray_seed_hit(const SceneView &sv, const d3 &o, c
   big_list_select_test(sv, o, d, rf, best, exact);
 }
 
+/* ---- ray reordering key ---------------------------------------------------------------------
+ * Secondary rays are incoherent; sorting a queue by a key built from the quantised origin and
+ * direction puts rays that walk the same part of the tree into the same warp.
+ * 18 origin bits (6 per axis, Morton order, relative to the guard box) and 6 direction bits
+ * (octahedral map, 8x8 cells); `mode` picks how they are interleaved. */
+__device__ __forceinline__ unsigned spread3(unsigned v) /* 6 bits -> every third bit */
+{
+  unsigned r = 0;
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    r |= ((v >> k) & 1u) << (3 * k);
+  return r;
+}
+
+__device__ __forceinline__ unsigned ray_sort_key(const SceneView &sv, const d3 &o, const d3 &d, int mode)
+{
+  unsigned q[3];
+  const float of[3] = { (float)o.x, (float)o.y, (float)o.z };
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+  {
+    const float ext = sv.guard_hi[k] - sv.guard_lo[k];
+    /* the scene box is the middle third of the guard box: zoom into it */
+    float u = (ext > 0.0f && ext < 1e30f) ? ((of[k] - sv.guard_lo[k]) / ext * 3.0f - 1.0f) : 0.0f;
+    u = fminf(fmaxf(u, 0.0f), 0.999999f);
+    q[k] = (unsigned)(u * 64.0f);
+  }
+  const unsigned morton = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2); /* 18 bits */
+  /* octahedral direction -> 3 + 3 bits */
+  float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+  const float inv = 1.0f / (fabsf(dx) + fabsf(dy) + fabsf(dz) + 1e-30f);
+  float px = dx * inv, py = dy * inv;
+  if (dz < 0.0f)
+  {
+    const float ox_ = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f);
+    const float oy_ = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);
+    px = ox_; py = oy_;
+  }
+  const unsigned du = (unsigned)fminf(fmaxf((px * 0.5f + 0.5f) * 8.0f, 0.0f), 7.0f);
+  const unsigned dv = (unsigned)fminf(fmaxf((py * 0.5f + 0.5f) * 8.0f, 0.0f), 7.0f);
+  const unsigned dir = (du << 3) | dv; /* 6 bits */
+  const unsigned octant = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+  switch (mode)
+  {
+  case 1: return ((morton >> 6) << 12) | (dir << 6) | (morton & 63u);  /* origin hi | dir | origin lo */
+  case 2: return (dir << 18) | morton;                                  /* direction major */
+  case 3: return (morton << 6) | dir;                                   /* origin major */
+  case 4: return (octant << 18) | morton;                               /* octant, then origin */
+  case 5: return ((morton >> 9) << 15) | (dir << 9) | (morton & 511u); /* origin 3 bits/axis | dir | rest */
+  default: return morton << 6;
+  }
+}
+
 /* warp-aggregated append: every lane of the warp must call this */
 __device__ __forceinline__ void wf_enqueue(const WfQueue &q, unsigned *count, bool want, int lane, const d3 &o, const d3 &d,
-                                           unsigned pid, float tr, float tg, float tb, const HitRec &seed)
+                                           unsigned pid, float tr, float tg, float tb, const HitRec &seed,
+                                           unsigned *keys = nullptr, unsigned key = 0u)
 {
   const unsigned m = __ballot_sync(WF_FULL, want);
   if (m == 0u)
@@ -90,11 +145,14 @@ __device__ __forceinline__ void wf_enqueue(const WfQueue &q, unsigned *count, bo
   if (want)
   {
     const unsigned i = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-    q.o_xy[i] = make_double2(o.x, o.y);
-    q.oz_dx[i] = make_double2(o.z, d.x);
-    q.d_yz[i] = make_double2(d.y, d.z);
-    q.path[i] = make_uint4(pid, __float_as_uint(tr), __float_as_uint(tg), __float_as_uint(tb));
-    q.hit[i] = pack_hit(seed);
+    /* queue traffic is streamed once: evict-first, so it does not push the BVH out of L2 */
+    __stcs(q.o_xy + i, make_double2(o.x, o.y));
+    __stcs(q.oz_dx + i, make_double2(o.z, d.x));
+    __stcs(q.d_yz + i, make_double2(d.y, d.z));
+    __stcs(q.path + i, make_uint4(pid, __float_as_uint(tr), __float_as_uint(tg), __float_as_uint(tb)));
+    __stcs(q.hit + i, pack_hit(seed));
+    if (keys)
+      __stcs(keys + i, key);
   }
 }
 
@@ -162,8 +220,7 @@ __global__ void __launch_bounds__(128) k_wf_generate(const __grid_constant__ Ren
  * V (variant bits): 1 = the double-precision ray is NOT kept in registers during the walk but
  * re-read from the queue at every leaf (fewer registers -> more warps per SM);
  * 2 = streaming (evict-first) loads/stores for queue data; 4 = whole traversal stack in local
- * memory (no shared-memory top); 8 = postponed leaf: a lane that reaches a leaf stashes it and
- * keeps walking (speculatively) until it meets a second leaf, so more lanes stay in the node phase. */
+ * memory (no shared-memory top); 8 = BVH4 (128-byte nodes, rtb_internal.h); 16 = compressed BVH4 (64-byte nodes). */
 template <int V> struct WfTraceCfg { static constexpr int blocks = (V & 1) ? 10 : 8; static constexpr int sd = (V & 4) ? 0 : WF_SMEM_STACK; };
 
 __device__ __forceinline__ double2 wf_ld(const double2 *p, bool stream)
@@ -178,9 +235,10 @@ __device__ __forceinline__ uint4 wf_ld(const uint4 *p, bool stream)
 template <bool STATS, int V>
 __global__ void __launch_bounds__(128, WfTraceCfg<V>::blocks)
 k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
-           unsigned long long *totals, int refill_idle, int node_exit)
+           unsigned long long *totals, int refill_idle, int node_exit, const unsigned *__restrict__ perm)
 {
-  constexpr bool RELOAD = (V & 1) != 0, STREAM = (V & 2) != 0, STASH = (V & 8) != 0;
+  constexpr bool RELOAD = (V & 1) != 0, STREAM = (V & 2) != 0;
+  constexpr int WIDE = (V & 16) ? 2 : ((V & 8) ? 1 : 0);
   constexpr int SD = WfTraceCfg<V>::sd;
   __shared__ int2 s_stack[SD > 0 ? SD : 1][128];
   const int lane = threadIdx.x & 31;
@@ -204,7 +262,6 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
   WalkStack<SD> stack = { &s_stack[0][threadIdx.x], stack_mem, 128 };
   int sp = 0;
   int cur = RTB_REF_NONE;
-  int stash = RTB_REF_NONE; /* STASH: a leaf waiting for the next leaf phase */
   unsigned node_visits = 0, prim_tests = 0;
 
   while (true)
@@ -230,10 +287,10 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
       const unsigned mine = next + (unsigned)__popc(bidle & ((1u << lane) - 1u));
       if (!active && mine < end)
       {
-        ray = mine;
-        const double2 a = wf_ld(q.o_xy + mine, STREAM), b = wf_ld(q.oz_dx + mine, STREAM), c = wf_ld(q.d_yz + mine, STREAM);
+        ray = perm ? __ldcs(perm + mine) : mine;
+        const double2 a = wf_ld(q.o_xy + ray, STREAM), b = wf_ld(q.oz_dx + ray, STREAM), c = wf_ld(q.d_yz + ray, STREAM);
         d3 o_ = d3_make(a.x, a.y, b.x), d_ = d3_make(b.y, c.x, c.y);
-        best = unpack_hit(wf_ld(q.hit + mine, STREAM));
+        best = unpack_hit(wf_ld(q.hit + ray, STREAM));
         rayf_basic(o_, d_, rf);
         if (rayf_walk_setup(sv, o_, d_, best, rf))
         {
@@ -268,7 +325,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         while (cur >= 0 && cur != RTB_REF_NONE)
         {
           if (STATS) node_visits++;
-          int nxt = node_step(sv, rf, cur, stack, sp);
+          int nxt = node_step_w<SD, WIDE>(sv, rf, cur, stack, sp);
           cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
         }
       }
@@ -277,11 +334,6 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         /* leave the node phase as soon as fewer than node_exit lanes are still at inner nodes */
         while (true)
         {
-          if (STASH && cur < 0 && stash == RTB_REF_NONE)
-          {
-            stash = cur;
-            cur = stack_pop(rf, stack, sp);
-          }
           const bool at_node = cur >= 0 && cur != RTB_REF_NONE;
           const unsigned bnode = __ballot_sync(WF_FULL, at_node);
           if (bnode == 0u)
@@ -289,41 +341,13 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
           if (at_node)
           {
             if (STATS) node_visits++;
-            int nxt = node_step(sv, rf, cur, stack, sp);
+            int nxt = node_step_w<SD, WIDE>(sv, rf, cur, stack, sp);
             cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
           }
           if (__popc(bnode) < node_exit)
             break;
         }
       }
-      if (STASH)
-      {
-        /* the leaf to test now: the stashed one first (it was met first) */
-        if (stash == RTB_REF_NONE && cur < 0)
-        {
-          stash = cur;
-          cur = stack_pop(rf, stack, sp);
-        }
-        if (stash != RTB_REF_NONE)
-        {
-          if (RELOAD)
-          {
-            const double2 a = q.o_xy[ray], b = q.oz_dx[ray], c = q.d_yz[ray];
-            o = d3_make(a.x, a.y, b.x);
-            d = d3_make(b.y, c.x, c.y);
-          }
-          const int code = ~stash;
-          const int first = code >> 3, count = (code & 7) + 1;
-          for (int k = 0; k < count; k++)
-            test_prim(load_prim(sv.prims, first + k), first + k, o, d, best);
-          if (STATS) prim_tests += (unsigned)count;
-          rayf_update_tmax(rf, best);
-          stash = RTB_REF_NONE;
-          /* an inner node popped speculatively may be out of range now: it is simply visited
-           * (its children fail the slab test); a speculatively popped LEAF is kept */
-        }
-      }
-      else
       if (cur < 0)
       {
         if (RELOAD)
@@ -340,7 +364,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         rayf_update_tmax(rf, best);
         cur = stack_pop(rf, stack, sp);
       }
-      if (active && cur == RTB_REF_NONE && stash == RTB_REF_NONE)
+      if (active && cur == RTB_REF_NONE)
       {
         if (STREAM)
           __stcs(q.hit + ray, pack_hit(best));
@@ -363,13 +387,13 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
 template <int V>
 static void launch_trace(bool stats, int blocks_per_sm_unused, int sm_count, cudaStream_t stream, const SceneView &sv,
                          const WfQueue &q, const unsigned *n_ptr, unsigned *fetch, unsigned long long *totals,
-                         int refill_idle, int node_exit)
+                         int refill_idle, int node_exit, const unsigned *perm)
 {
   const int blocks = sm_count * WfTraceCfg<V>::blocks;
   if (stats)
-    k_wf_trace<true, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit);
+    k_wf_trace<true, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
   else
-    k_wf_trace<false, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit);
+    k_wf_trace<false, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
 }
 
 /* ---- shading of a whole queue ------------------------------------------------------------------
@@ -377,7 +401,7 @@ static void launch_trace(bool stats, int blocks_per_sm_unused, int sm_count, cud
  * path goes on, the oversized-list test of the NEXT ray and a warp-aggregated append. */
 __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ RenderArgs A, int wave, int depth, WfQueue qin,
                                                   const unsigned *__restrict__ n_in, WfQueue qout, unsigned *n_out,
-                                                  float4 *__restrict__ planes)
+                                                  float4 *__restrict__ planes, unsigned *keys_out, int sort_mode)
 {
   const int lane = threadIdx.x & 31;
   const unsigned n = *n_in;
@@ -401,9 +425,9 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ Render
     seed.t = DBL_MAX; seed.gid = 0x7FFFFFFF; seed.slot = 0;
     if (i < n)
     {
-      const uint4 p = qin.path[i];
-      const double2 a = qin.o_xy[i], b = qin.oz_dx[i], c = qin.d_yz[i];
-      const HitRec best = unpack_hit(qin.hit[i]);
+      const uint4 p = __ldcs(qin.path + i);
+      const double2 a = __ldcs(qin.o_xy + i), b = __ldcs(qin.oz_dx + i), c = __ldcs(qin.d_yz + i);
+      const HitRec best = unpack_hit(__ldcs(qin.hit + i));
       pid = p.x;
       st.o = d3_make(a.x, a.y, b.x);
       st.d = d3_make(b.y, c.x, c.y);
@@ -412,18 +436,19 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ Render
       const unsigned plane = pid / n_px;
       const unsigned pixel = pid - plane * n_px;
       const unsigned sample = (unsigned)(A.s_begin + (int)plane * A.chunk + wave);
-      float4 acc = planes[pid];
+      float4 acc = __ldcs(planes + pid);
       const float4 before = acc;
       pc.rays++;
       pc.rays_hit++;
       path_shade(A, st, best, pixel, sample, acc.x, acc.y, acc.z, pc, nullptr);
       if (__float_as_uint(acc.x) != __float_as_uint(before.x) || __float_as_uint(acc.y) != __float_as_uint(before.y) ||
           __float_as_uint(acc.z) != __float_as_uint(before.z))
-        planes[pid] = acc;
+        __stcs(planes + pid, acc);
       if (st.alive)
         ray_seed_hit(A.sv, st.o, st.d, seed, exact);
     }
-    wf_enqueue(qout, n_out, st.alive, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed);
+    wf_enqueue(qout, n_out, st.alive, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed, keys_out,
+               (keys_out && st.alive) ? ray_sort_key(A.sv, st.o, st.d, sort_mode) : 0u);
   }
   wf_add_counters(A.counters, lane, pc.rays, pc.rays_hit, exact, 0ull, 0ull);
 }
@@ -447,12 +472,18 @@ __global__ void k_wf_sum_planes(const float4 *__restrict__ planes, int n_planes,
 
 /* ---- host ---------------------------------------------------------------------------------- */
 
+__global__ void k_wf_iota(unsigned *v, unsigned n)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    v[i] = i;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, float *d_accum, cudaStream_t stream,
               bool stats, unsigned long long &launches)
 {
-  const int spp = A.s_end - A.s_begin;
   const size_t n_px = (size_t)A.width * A.height;
   const size_t slots = n_px * (size_t)A.splits;
   if (slots >= (1ull << 31))
@@ -462,10 +493,35 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   }
   const int n_bounces = A.max_depth + 1;
 
-  /* one allocation: 2 queues x 5 arrays of 16 B, the planes, the per-wave counters */
+  /* tuning word (desc->reserved): bits 0-7 refill threshold, 8-15 node-phase exit threshold,
+   * 16-23 trace kernel variant; desc->reserved2: ray sorting mode (0 = off) */
+  const int refill_idle = ((desc->reserved & 0xFF) > 0 && (desc->reserved & 0xFF) <= 32) ? (desc->reserved & 0xFF) : 8;
+  int node_exit = (desc->reserved >> 8) & 0xFF;
+  int variant = (desc->reserved >> 16) & 0xFF;
+  if (desc->reserved == 0)
+  {
+    /* measured defaults (profiles/r1_wf_tuning.md) */
+    node_exit = 16;
+    variant = 22; /* compressed BVH4 + local stack + streaming queue loads */
+  }
+  if (node_exit == 0xFF)
+    node_exit = 0; /* pure while-while */
+  const int sort_mode = desc->reserved2 & 0xFF;
+  const int sort_from = 1;                                           /* primary rays are coherent already */
+  const int sort_until = (desc->reserved2 >> 8) & 0xFF ? (desc->reserved2 >> 8) & 0xFF : 255;
+
+  /* one allocation: 2 queues x 5 arrays of 16 B, the planes, sort buffers, the per-wave counters */
   const size_t arr = align_up(slots * 16, 256);
+  const size_t arr4 = align_up(slots * 4, 256);
   const size_t ctr_bytes = align_up(sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), 256);
-  const size_t need = arr * 11 + ctr_bytes;
+  size_t sort_tmp_bytes = 0;
+  if (sort_mode)
+  {
+    unsigned *nul = nullptr;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, nul, nul, nul, nul, (int)slots, 0, 24, stream);
+    sort_tmp_bytes = align_up(sort_tmp_bytes, 256);
+  }
+  const size_t need = arr * 11 + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0);
   if (scene->wf_bytes < need)
   {
     if (scene->d_wf)
@@ -488,24 +544,24 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   float4 *planes = reinterpret_cast<float4 *>(p); p += arr;
   unsigned *counts = reinterpret_cast<unsigned *>(p);            /* [n_bounces + 2] queue lengths */
   unsigned *fetch = counts + (n_bounces + 2);                    /* [n_bounces + 2] trace fetch cursors */
+  p += ctr_bytes;
+  unsigned *keys = nullptr, *keys_sorted = nullptr, *iota = nullptr, *perm = nullptr;
+  void *sort_tmp = nullptr;
+  if (sort_mode)
+  {
+    keys = reinterpret_cast<unsigned *>(p); p += arr4;
+    keys_sorted = reinterpret_cast<unsigned *>(p); p += arr4;
+    iota = reinterpret_cast<unsigned *>(p); p += arr4;
+    perm = reinterpret_cast<unsigned *>(p); p += arr4;
+    sort_tmp = p;
+    k_wf_iota<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(iota, (unsigned)slots);
+    launches++;
+  }
 
   RTB_CUDA(cudaMemsetAsync(planes, 0, slots * 16, stream));
 
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device);
-  /* tuning word (desc->reserved): bits 0-7 refill threshold, 8-15 node-phase exit threshold,
-   * 16-23 trace kernel variant */
-  const int refill_idle = ((desc->reserved & 0xFF) > 0 && (desc->reserved & 0xFF) <= 32) ? (desc->reserved & 0xFF) : 8;
-  int node_exit = (desc->reserved >> 8) & 0xFF;
-  int variant = (desc->reserved >> 16) & 0xFF;
-  if (desc->reserved == 0)
-  {
-    /* measured defaults (profiles/r1_wf_tuning.md) */
-    node_exit = 16;
-    variant = 2;
-  }
-  if (node_exit == 0xFF)
-    node_exit = 0; /* pure while-while */
   const int shade_blocks = sm_count * 16;
   const long long gen_warps = (long long)A.n_tiles * A.splits;
   const int gen_blocks = (int)((gen_warps * 32 + 127) / 128);
@@ -518,24 +574,34 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     for (int b = 0; b < n_bounces; b++)
     {
       const WfQueue &qi = q[b & 1], &qo = q[(b + 1) & 1];
+      const bool sorted_in = sort_mode && b >= sort_from && b <= sort_until;        /* queue b was sorted */
+      const bool sort_out = sort_mode && b + 1 >= sort_from && b + 1 <= sort_until && b + 1 < n_bounces;
+      const unsigned *use_perm = sorted_in ? perm : nullptr;
       switch (variant)
       {
-      case 2: launch_trace<2>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 4: launch_trace<4>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 6: launch_trace<6>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 8: launch_trace<8>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 10: launch_trace<10>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 12: launch_trace<12>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 14: launch_trace<14>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      case 1: launch_trace<1>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
-      default: launch_trace<0>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit); break;
+      case 2: launch_trace<2>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 4: launch_trace<4>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 18: launch_trace<18>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 22: launch_trace<22>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 10: launch_trace<10>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 14: launch_trace<14>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 6: launch_trace<6>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      default: launch_trace<0>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       }
-      k_wf_shade<<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes);
+      if (sort_out) /* slots beyond the queue's end keep the largest key and sort to the back */
+        RTB_CUDA(cudaMemsetAsync(keys, 0xFF, slots * 4, stream));
+      k_wf_shade<<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes,
+                                                   sort_out ? keys : nullptr, sort_mode);
       launches += 2;
+      if (sort_out)
+      {
+        size_t tmp = sort_tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(sort_tmp, tmp, keys, keys_sorted, iota, perm, (int)slots, 0, 24, stream);
+        launches += 4;
+      }
     }
     RTB_CUDA(cudaGetLastError());
   }
-  (void)spp;
   k_wf_sum_planes<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(planes, A.splits, (unsigned)n_px, d_accum);
   RTB_CUDA(cudaGetLastError());
   launches++;

@@ -64,7 +64,7 @@ def test_golden_hits_on_device(gpu_api):
     objs = gpu_api.scene_default(320, 180)
     rays = random_rays_in_room(np.random.default_rng(105), 3000)
     with gpu_api.Scene(objs) as sc:
-        for mode in (1, 2, 3, 0):  # BVH, BVH + FP32 pre-test, while-while, brute force
+        for mode in (1, 2, 3, 4, 5, 0):  # BVH, BVH + FP32 pre-test, while-while, BVH4, compressed BVH4, brute force
             got = sc.trace_rays(rays, use_bvh=mode)
             assert np.array_equal(got["ids"], g["ids"]), mode
             # same double arithmetic without contraction on both sides: bit-identical
@@ -100,7 +100,15 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
         _, base, c0 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=4, planes=planes), want_accum=True)
         _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes), want_accum=True)
         _, acc2, c2 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=1), want_accum=True)
+        wide = (10 << 16) | (16 << 8)  # BVH4 walk
+        _, acc3, c3 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=wide), want_accum=True)
+        wideq = (22 << 16) | (16 << 8)  # compressed BVH4 walk
+        _, acc5, c5 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=wideq), want_accum=True)
+        assert np.array_equal(acc5, base) and c5.rays == c0.rays
+        _, acc4, c4 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune2=3), want_accum=True)
     assert np.array_equal(acc, base) and np.array_equal(acc2, base)
+    assert np.array_equal(acc3, base) and c3.rays == c0.rays and c3.node_visits < c0.node_visits
+    assert np.array_equal(acc4, base) and c4.rays == c0.rays  # sorted queues: same sums
     assert c0.rays == c1.rays == c2.rays and c0.paths == c1.paths == W * H * spp
     assert c0.rays_intersected == c1.rays_intersected
     assert c1.node_visits == c0.node_visits and c1.prim_tests == c0.prim_tests
@@ -135,6 +143,8 @@ def test_full_size_properties(gpu_api):
         # 4k random rays: BVH == brute force over 1M triangles
         rays = random_rays_in_room(np.random.default_rng(9), 4096)
         bvh, brute = sc.trace_rays(rays, use_bvh=1), sc.trace_rays(rays, use_bvh=0)
+        bvh4 = sc.trace_rays(rays, use_bvh=4)
+        bvh4q = sc.trace_rays(rays, use_bvh=5)
     # (a path that Russian roulette stops on a non-emissive surface contributes exactly 0)
     assert np.isfinite(ab).all() and (ab >= 0).all() and (ab.reshape(-1, 3).sum(axis=1) > 0).mean() > 0.3
     np.testing.assert_allclose(a + b, ab, rtol=1e-5, atol=1e-6)
@@ -142,3 +152,5 @@ def test_full_size_properties(gpu_api):
     assert 2.0 < cab.rays / cab.paths < 7.0
     for k in ("ids", "prims", "t", "points", "normals"):
         assert np.array_equal(bvh[k], brute[k]), k
+        assert np.array_equal(bvh4[k], brute[k]), k
+        assert np.array_equal(bvh4q[k], brute[k]), k
