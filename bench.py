@@ -137,11 +137,14 @@ def measured_peaks():
 
 
 def ncu_traffic(workload):
-    """dram bytes per k_render launch from the committed ncu capture, if any"""
+    """dram bytes (read + write) summed over the k_wf_trace launches of ONE step, from the
+    committed ncu capture of the same command (profiles/ncu_traffic.json), if any"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get(workload)
+            d = json.load(f)
+        if d.get("kernel") == "k_wf_trace":
+            return d.get(workload)
     return None
 
 
@@ -149,15 +152,17 @@ def ncu_traffic(workload):
 
 def cpu_sample(name, W, H, depth):
     """a bounded sample of the same workload for the host cores: same scene, reduced frame"""
-    return {"c1": (160, 90, 8), "c2": (48, 27, 1), "c3": (32, 18, 1), "c4": (48, 27, 1), "c5": (32, 32, 1)}[name]
+    # sized for roughly 10-20 s of host work per pass (the brute-force loop visits every primitive)
+    return {"c1": (320, 180, 400), "c2": (480, 270, 1), "c3": (64, 36, 1), "c4": (480, 270, 1), "c5": (256, 256, 4)}[name]
 
 
 def run_cpu_step(api, ol, name, source, depth, step, threads):
     """one pass of the reference algorithm over the bounded sample -> (rays, seconds, kind).
-    Spheres-only workloads with the reference's own depth run the UNMODIFIED reference
-    (oracle/_ref, one single-threaded process per core: its OpenMP build serialises on
-    rand()); the mesh workload runs the oracle port (the reference has
-    no live mesh path), OpenMP over rows with the keyed RNG."""
+    The oracle port (oracle/oracle.c: the reference's brute-force intersect() and trace_path()
+    restated, bit-identical to the reference for sphere scenes) with OpenMP over rows and the
+    keyed RNG.  The unmodified reference cannot run these workloads: it has no live mesh path
+    (c3), its dielectric split is 2^depth (c5) and its OpenMP build serialises on rand()
+    (SURVEY.md section 6)."""
     w, h, spp = cpu_sample(name, 0, 0, depth)
     cam = api.init_camera(w, h)
     t0 = time.perf_counter()
@@ -332,11 +337,22 @@ def main_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = rays_step / te[0].item() / 1e3
 
-    # ---- roofline of the dominant kernel (k_render) --------------------------------------------
+    # ---- roofline of the dominant kernel (k_wf_trace) -----------------------------------------
+    # its launches of one step (one per bounce and wave) are timed live with CUDA events on the
+    # launching stream (rtb_counters.trace_ms); L2 flushed before each pass like the timed steps
+    trace_ms_list, step_ms_list, trace_launches = [], [], 0
+    for i in range(min(args.steps, 3)):
+        flush.fill_(i & 0xFF)
+        c = scene.render_accum(cam, desc, accum.data_ptr(), stream=stream.cuda_stream, want_counters=True)
+        trace_ms_list.append(c.trace_ms)
+        step_ms_list.append(c.gpu_ms)
+        trace_launches = int(c.trace_launches)
+    trace_ms = sum(trace_ms_list) / len(trace_ms_list)
+    trace_share = trace_ms / (sum(step_ms_list) / len(step_ms_list))
     flops_ray, bytes_ray = algorithmic_cost(args.workload, n_prims or 38, S, P)
     peak, peak_src = measured_peaks()
-    achieved_gbs = hit_rank * bytes_ray / (kernel_ms * 1e-3) / 1e9
-    achieved_tflops = hit_rank * flops_ray / (kernel_ms * 1e-3) / 1e12
+    achieved_gbs = hit_rank * bytes_ray / (trace_ms * 1e-3) / 1e9
+    achieved_tflops = hit_rank * flops_ray / (trace_ms * 1e-3) / 1e12
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
 
@@ -357,16 +373,20 @@ def main_gpu(args):
             "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {text}", "width": W, "height": H, "spp_per_gpu": spp,
                        "max_depth": depth, "seed": SEED, "l2": "512 MB memset between timed steps (L2 flushed)",
-                       "parallelism": f"spp-sharded x{world}, one NCCL reduce", "kernel": "megakernel"},
+                       "parallelism": f"spp-sharded x{world}, one NCCL reduce",
+                       "kernel": "wavefront (k_wf_generate / k_wf_trace / k_wf_shade), compressed BVH4"},
             "paths_per_s": paths_per_s, "rays_per_step": rays_step, "rays_per_path": rays_step / (world * W * H * spp),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": te[0].item(), "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(W * H * 3), "api": "render_scene()/render_ex() of libraytracer_b200.so" if world == 1
                     else "rtb_scene_create + rtb_render_accum + NCCL reduce + rtb_tonemap + D2H"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
-                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": "k_render",
-                         "kernel_ms": kernel_ms, "bytes_per_intersected_ray": bytes_ray,
-                         "intersected_rays_per_launch": hit_rank,
+                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": "k_wf_trace",
+                         "kernel_ms_per_step": trace_ms, "launches_per_step": trace_launches,
+                         "avg_launch_ms": trace_ms / max(1, trace_launches), "share_of_step": trace_share,
+                         "step_kernels_ms": kernel_ms, "bytes_per_intersected_ray": bytes_ray,
+                         "intersected_rays_per_step": hit_rank,
+                         "achieved_def": "intersected rays of one step x SURVEY 8(d) bytes per ray / summed k_wf_trace time of the step",
                          "note": "algorithmic bytes are L2/L1-resident BVH+primitive fetches (SURVEY 8d); HBM peak is the only measured memory denominator"},
             "roofline_fp32": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                               "frac": achieved_tflops / fp32_peak, "flops_per_intersected_ray": flops_ray,

@@ -82,6 +82,9 @@ typedef struct
   unsigned long long launches;        /* kernels launched by the call */
   float gpu_ms;                       /* CUDA-event time of the call's kernels on `stream` */
   float build_ms;                     /* scene create only: upload + marshal + BVH build */
+  float trace_ms;                     /* wavefront kernels: CUDA-event time summed over the k_wf_trace launches */
+  float shade_ms;                     /* wavefront kernels: same for k_wf_generate + k_wf_shade */
+  unsigned long long trace_launches;  /* number of k_wf_trace launches */
 } rtb_counters;
 
 typedef struct

@@ -442,6 +442,8 @@ __device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, i
 
 /* One compressed BVH4 node (Bvh4QNode): slab distances straight from the quantised planes,
  * t = q * (2^e / d) + (origin - o) / d */
+/* byte k of w as a float: I2F.U8 with a byte selector, one instruction (a PRMT + FADD
+ * formulation that avoids the conversion pipe measured 4 % slower) */
 __device__ __forceinline__ float qbyte(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
 
 template <int SD>

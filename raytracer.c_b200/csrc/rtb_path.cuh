@@ -166,6 +166,6 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
 /* rtb_wavefront.cu: render [A.s_begin, A.s_end) with the wavefront kernels into d_accum
  * (A.splits planes of A.chunk samples each must be set) */
 int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, float *d_accum, cudaStream_t stream,
-              bool stats, unsigned long long &launches);
+              bool stats, unsigned long long &launches, float *phase_ms);
 
 #endif /* RTB_PATH_CUH */

@@ -650,7 +650,9 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
    * Megakernels: enough threads to fill 148 SMs a few times over even for small frames.
    * Wavefront: ~8 M paths in flight per wave (1.4 GB of queues), so the deep bounces still have
    * enough rays to fill the machine. */
-  const bool wavefront = desc->kernel == 6;
+  /* kernel 0 = auto = wavefront: faster than every megakernel variant on all five benchmark
+   * configurations */
+  const bool wavefront = desc->kernel == 6 || desc->kernel == 0;
   const long long want_threads = wavefront ? (8ll << 20) : 148ll * 2048 * 2;
   int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);
   if (desc->planes > 0)
@@ -663,6 +665,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   A.splits = splits;
 
   unsigned long long launches = 0;
+  float phase_ms[3] = { 0.0f, 0.0f, 0.0f };
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (counters)
   {
@@ -680,7 +683,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   {
     if (wavefront)
     {
-      int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr, launches);
+      int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr, launches, counters ? phase_ms : nullptr);
       if (wrc != RTB_OK)
         return wrc;
     }
@@ -725,7 +728,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
       if (counters) k_render_pw<true><<<blocks, threads, 0, stream>>>(A);
       else k_render_pw<false><<<blocks, threads, 0, stream>>>(A);
       break;
-    default: /* 0, 4: while-while walk + select-then-test, 64 registers -> 32 warps/SM */
+    default: /* 4: while-while walk + select-then-test, 64 registers -> 32 warps/SM */
       if (counters) k_render<true, 2><<<blocks, threads, 0, stream>>>(A);
       else k_render<false, 2><<<blocks, threads, 0, stream>>>(A);
       break;
@@ -757,6 +760,9 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     counters->launches = launches;
     RTB_CUDA(cudaEventElapsedTime(&counters->gpu_ms, ev0, ev1));
     counters->build_ms = scene->info.build_ms;
+    counters->trace_ms = phase_ms[0];
+    counters->shade_ms = phase_ms[1];
+    counters->trace_launches = (unsigned long long)phase_ms[2];
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }

@@ -27,6 +27,7 @@
 #include "rtb_path.cuh"
 
 #include <algorithm>
+#include <vector>
 #include <cub/cub.cuh>
 
 #define WF_FULL 0xFFFFFFFFu
@@ -482,7 +483,7 @@ __global__ void k_wf_iota(unsigned *v, unsigned n)
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, float *d_accum, cudaStream_t stream,
-              bool stats, unsigned long long &launches)
+              bool stats, unsigned long long &launches, float *phase_ms)
 {
   const size_t n_px = (size_t)A.width * A.height;
   const size_t slots = n_px * (size_t)A.splits;
@@ -566,6 +567,16 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   const long long gen_warps = (long long)A.n_tiles * A.splits;
   const int gen_blocks = (int)((gen_warps * 32 + 127) / 128);
 
+  /* per-kernel timing (only with counters): events around every trace launch */
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() {
+    if (!phase_ms)
+      return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    ev.push_back(e);
+  };
   for (int wave = 0; wave < A.chunk; wave++)
   {
     RTB_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), stream));
@@ -577,6 +588,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       const bool sorted_in = sort_mode && b >= sort_from && b <= sort_until;        /* queue b was sorted */
       const bool sort_out = sort_mode && b + 1 >= sort_from && b + 1 <= sort_until && b + 1 < n_bounces;
       const unsigned *use_perm = sorted_in ? perm : nullptr;
+      mark();
       switch (variant)
       {
       case 2: launch_trace<2>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
@@ -588,6 +600,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       case 6: launch_trace<6>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       default: launch_trace<0>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       }
+      mark();
       if (sort_out) /* slots beyond the queue's end keep the largest key and sort to the back */
         RTB_CUDA(cudaMemsetAsync(keys, 0xFF, slots * 4, stream));
       k_wf_shade<<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes,
@@ -605,5 +618,24 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   k_wf_sum_planes<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(planes, A.splits, (unsigned)n_px, d_accum);
   RTB_CUDA(cudaGetLastError());
   launches++;
+  if (phase_ms)
+  {
+    /* ev = [t0 trace t1] shade/generate [t2 trace t3] ...: odd gaps are trace launches */
+    mark();
+    RTB_CUDA(cudaEventSynchronize(ev.back()));
+    float trace = 0.0f, total = 0.0f;
+    for (size_t k = 0; k + 1 < ev.size(); k += 2)
+    {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+      trace += ms;
+    }
+    cudaEventElapsedTime(&total, ev.front(), ev.back());
+    phase_ms[0] = trace;
+    phase_ms[1] = total - trace; /* generate of later waves + shade + sum (the first generate is before ev[0]) */
+    phase_ms[2] = (float)(ev.size() / 2);
+    for (cudaEvent_t e : ev)
+      cudaEventDestroy(e);
+  }
   return RTB_OK;
 }

@@ -99,7 +99,7 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
     with gpu_api.Scene(holder) as sc:
         _, base, c0 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=4, planes=planes), want_accum=True)
         _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes), want_accum=True)
-        _, acc2, c2 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=1), want_accum=True)
+        _, acc2, c2 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=(2 << 16) | (16 << 8) | 1), want_accum=True)  # BVH2 walk, refill at 1 idle lane
         wide = (10 << 16) | (16 << 8)  # BVH4 walk
         _, acc3, c3 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=wide), want_accum=True)
         wideq = (22 << 16) | (16 << 8)  # compressed BVH4 walk
@@ -111,7 +111,7 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
     assert np.array_equal(acc4, base) and c4.rays == c0.rays  # sorted queues: same sums
     assert c0.rays == c1.rays == c2.rays and c0.paths == c1.paths == W * H * spp
     assert c0.rays_intersected == c1.rays_intersected
-    assert c1.node_visits == c0.node_visits and c1.prim_tests == c0.prim_tests
+    assert c2.node_visits == c0.node_visits and c2.prim_tests == c0.prim_tests  # same BVH2, same order
 
 
 def test_wavefront_depth_zero_and_empty(gpu_api):
