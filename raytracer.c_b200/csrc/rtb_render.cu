@@ -648,12 +648,19 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
    * separately and summed in order -- this fixes the floating-point summation order, so every
    * kernel variant gives the same bits for the same number of planes.
    * Megakernels: enough threads to fill 148 SMs a few times over even for small frames.
-   * Wavefront: ~8 M paths in flight per wave (1.4 GB of queues), so the deep bounces still have
-   * enough rays to fill the machine. */
-  /* kernel 0 = auto = wavefront: faster than every megakernel variant on all five benchmark
-   * configurations */
+   * Wavefront: up to 64 M paths in flight per wave (11.7 GB of queues out of 180 GB): the deep
+   * bounces then still have enough rays to fill 148 SMs and the per-launch tail of the
+   * persistent trace kernel is amortised (measured C3: 8 M 3.07, 33 M 3.48, 66 M 3.61 Grays/s);
+   * never more than a quarter of the free device memory. */
   const bool wavefront = desc->kernel == 6 || desc->kernel == 0;
-  const long long want_threads = wavefront ? (8ll << 20) : 148ll * 2048 * 2;
+  long long want_threads = 148ll * 2048 * 2;
+  if (wavefront)
+  {
+    size_t free_b = 0, total_b = 0;
+    RTB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    want_threads = std::min<long long>(64ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 192));
+    want_threads = std::max<long long>(want_threads, (long long)n_px);
+  }
   int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);
   if (desc->planes > 0)
     splits = std::min(desc->planes, 1024);

@@ -34,6 +34,9 @@
 #ifndef WF_SMEM_STACK
 #define WF_SMEM_STACK 8
 #endif
+#ifndef WF_SHADE_BLOCKS
+#define WF_SHADE_BLOCKS 8
+#endif
 #ifndef WF_TRACE_BLOCKS_PER_SM
 #define WF_TRACE_BLOCKS_PER_SM 8
 #endif
@@ -182,7 +185,7 @@ __device__ __forceinline__ void wf_add_counters(unsigned long long *totals, int 
 /* ---- camera samples of one wave ------------------------------------------------------------
  * One thread per path slot; warps map to 8x4 pixel tiles of one plane so that the primary
  * rays a warp appends (and a trace warp later fetches together) are coherent. */
-__global__ void __launch_bounds__(128) k_wf_generate(const __grid_constant__ RenderArgs A, int wave, WfQueue q,
+__global__ void __launch_bounds__(128, 8) k_wf_generate(const __grid_constant__ RenderArgs A, int wave, WfQueue q,
                                                      unsigned *count)
 {
   const int lane = threadIdx.x & 31;
@@ -400,7 +403,7 @@ static void launch_trace(bool stats, int blocks_per_sm_unused, int sm_count, cud
 /* ---- shading of a whole queue ------------------------------------------------------------------
  * Thread i handles ray i: the body of trace_path after intersect() (path_shade), then, if the
  * path goes on, the oversized-list test of the NEXT ray and a warp-aggregated append. */
-__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ RenderArgs A, int wave, int depth, WfQueue qin,
+__global__ void __launch_bounds__(128, WF_SHADE_BLOCKS) k_wf_shade(const __grid_constant__ RenderArgs A, int wave, int depth, WfQueue qin,
                                                   const unsigned *__restrict__ n_in, WfQueue qout, unsigned *n_out,
                                                   float4 *__restrict__ planes, unsigned *keys_out, int sort_mode)
 {
