@@ -16,6 +16,7 @@
  *   rtb_trace_rays         intersect() for arbitrary rays (raytracer.c:393-464): parity probe
  *   rtb_path_records       per-path vertex records: parity probe for the 1-bounce check
  *   rtb_philox4x32_10      random_double()'s replacement (raytracer.c:227): KAT probe
+ *   rtb_probe_l2_bandwidth no reference counterpart: measures the L2 roofline denominator
  *
  * Array arguments named `objects` are arrays of the reference's own records:
  *   - flat sphere record `Object`, 88 bytes (raytracer.h:104-111):
@@ -127,6 +128,10 @@ int rtb_path_records(rtb_scene *scene, const double *camera12, const rtb_render_
                      int n_vertices, int32_t *ids, double *points, double *normals, double *dists,
                      float *radiance);
 int rtb_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, size_t n, uint32_t *out4, int device);
+
+/* measurement probe: read bandwidth of an L2-resident buffer of `bytes` (128-bit ld.global.cg from every SM,
+ * `iters` passes), in GB/s -- the denominator bench.py uses for the walk's L1/L2-served algorithmic bytes */
+int rtb_probe_l2_bandwidth(size_t bytes, int iters, int device, float *gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ LIB_HOST = os.path.join(_HERE, "libraytracer_b200.so")
 RTB_SYMBOLS = [
     "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_scene_create_objects", "rtb_scene_create",
     "rtb_scene_info_get", "rtb_scene_destroy", "rtb_render_accum", "rtb_tonemap", "rtb_render",
-    "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10",
+    "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth",
 ]
 # the reference's exported surface (raytracer.h:135-164) plus the documented extensions
 HOST_SYMBOLS = [
@@ -75,6 +75,7 @@ def _bind(cu, host):
     cu.rtb_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int] + [C.c_void_p] * 6
     cu.rtb_path_records.argtypes = [C.c_void_p, dp, C.POINTER(abi.RtbRenderDesc), C.c_int, C.c_int] + [C.c_void_p] * 5
     cu.rtb_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    cu.rtb_probe_l2_bandwidth.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]
 
     host.init_camera.argtypes = [C.POINTER(abi.Camera), abi.Vec3, abi.Vec3, C.POINTER(abi.Options)]
     host.init_camera.restype = None
@@ -324,6 +325,14 @@ def tonemap(d_accum_ptr, width, height, total_samples, d_fb_ptr, device=0, strea
     cu, _ = load()
     _check(cu.rtb_tonemap(C.c_void_p(d_accum_ptr), width, height, total_samples, C.c_void_p(d_fb_ptr), device,
                           C.c_void_p(stream or 0)), "rtb_tonemap")
+
+
+def probe_l2_bandwidth(nbytes=32 << 20, iters=50, device=0):
+    """read bandwidth (GB/s) of an L2-resident buffer: the denominator for the walk's algorithmic bytes"""
+    cu, _ = load()
+    out = C.c_float(0.0)
+    _check(cu.rtb_probe_l2_bandwidth(nbytes, iters, device, C.byref(out)), "rtb_probe_l2_bandwidth")
+    return float(out.value)
 
 
 def philox(ctr, key, device=0):

@@ -324,22 +324,43 @@ __device__ __forceinline__ void rayf_update_tmax(RayF &rf, const HitRec &best)
 
 /* Traversal stack.  The first SD entries of every thread live in shared memory, laid out
  * [entry][thread] (conflict-free), the rest in local memory.  SD = 0 keeps everything in
- * local memory.  Entry = {reference, entry distance as float bits}. */
+ * local memory.  Entry = {reference, entry distance as float bits}.
+ * (Keeping the most recent entry in two registers so that a pop never waits for memory was
+ * measured 5 % slower: register pressure.) */
 template <int SD>
 struct WalkStack
 {
-  int2 *smem;  /* this thread's column: entry k at smem[k * blockDim.x]; unused when SD == 0 */
-  int2 *local; /* RTB_STACK_SIZE entries */
+  int2 *smem;  /* this thread's column: entry k at smem[k * stride]; unused when SD == 0 */
+  int2 *local; /* RTB_STACK_SIZE - SD entries */
   int stride;
-  __device__ __forceinline__ void put(int sp, int2 e) const
+  int sp;      /* entries in memory */
+  __device__ __forceinline__ void put(int at, int2 e) const
   {
-    if (SD > 0 && sp < SD) smem[sp * stride] = e;
-    else local[sp - SD] = e;
+    if (SD > 0 && at < SD) smem[at * stride] = e;
+    else local[at - SD] = e;
   }
-  __device__ __forceinline__ int2 get(int sp) const
+  __device__ __forceinline__ int2 get(int at) const
   {
-    if (SD > 0 && sp < SD) return smem[sp * stride];
-    return local[sp - SD];
+    if (SD > 0 && at < SD) return smem[at * stride];
+    return local[at - SD];
+  }
+  __device__ __forceinline__ void reset() { sp = 0; }
+  __device__ __forceinline__ void push(int2 e)
+  {
+    put(sp, e);
+    sp++;
+  }
+  /* the next subtree that can still contain a nearer hit; RTB_REF_NONE when done */
+  __device__ __forceinline__ int pop(const RayF &rf)
+  {
+    while (sp > 0)
+    {
+      sp--;
+      const int2 e = get(sp);
+      if (__int_as_float(e.y) <= rf.tmax)
+        return e.x;
+    }
+    return RTB_REF_NONE;
   }
 };
 
@@ -353,8 +374,8 @@ __device__ __forceinline__ void ld256_nc(const float4 *p, float4 &a, float4 &b)
 
 /* One inner node: tests both children, returns the reference to continue with
  * (RTB_REF_NONE if neither is hit) and pushes the farther one. */
-template <int SD>
-__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+template <class STK>
+__device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, int cur, STK &stack)
 {
   /* 64-byte node = two 256-bit loads (LDG.E.256, new on sm_100): half the L1 wavefronts of
    * four 128-bit loads -- the L1 data pipe was 60 % busy with node fetches
@@ -381,8 +402,7 @@ __device__ __forceinline__ int node_step(const SceneView &sv, const RayF &rf, in
   if (h0 && h1)
   {
     bool swap = c1min < c0min;
-    stack.put(sp, make_int2(swap ? r0 : r1, __float_as_int(swap ? c0min : c1min)));
-    sp++;
+    stack.push(make_int2(swap ? r0 : r1, __float_as_int(swap ? c0min : c1min)));
     return swap ? r1 : r0;
   }
   if (h0) return r0;
@@ -400,8 +420,8 @@ __device__ __forceinline__ void cswap(float &da, int &ra, float &db, int &rb)
   da = dt; db = du; ra = rt; rb = ru;
 }
 
-template <int SD>
-__device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+template <class STK>
+__device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, int cur, STK &stack)
 {
   const float4 *np = sv.nodes4 + 8 * (size_t)cur;
   float4 lox, hix, loy, hiy, loz, hiz, rr, spare;
@@ -434,9 +454,9 @@ __device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, i
   cswap(dist[1], ref[1], dist[2], ref[2]);
   if (dist[0] >= INF)
     return RTB_REF_NONE;
-  if (dist[3] < INF) { stack.put(sp, make_int2(ref[3], __float_as_int(dist[3]))); sp++; }
-  if (dist[2] < INF) { stack.put(sp, make_int2(ref[2], __float_as_int(dist[2]))); sp++; }
-  if (dist[1] < INF) { stack.put(sp, make_int2(ref[1], __float_as_int(dist[1]))); sp++; }
+  if (dist[3] < INF) stack.push(make_int2(ref[3], __float_as_int(dist[3])));
+  if (dist[2] < INF) stack.push(make_int2(ref[2], __float_as_int(dist[2])));
+  if (dist[1] < INF) stack.push(make_int2(ref[1], __float_as_int(dist[1])));
   return ref[0];
 }
 
@@ -446,8 +466,8 @@ __device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, i
  * formulation that avoids the conversion pipe measured 4 % slower) */
 __device__ __forceinline__ float qbyte(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
 
-template <int SD>
-__device__ __forceinline__ int node_step4q(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+template <class STK>
+__device__ __forceinline__ int node_step4q(const SceneView &sv, const RayF &rf, int cur, STK &stack)
 {
   const float4 *np = sv.nodes4q + 4 * (size_t)cur;
   float4 w0, w1, w2, w3;
@@ -481,35 +501,21 @@ __device__ __forceinline__ int node_step4q(const SceneView &sv, const RayF &rf, 
   cswap(dist[1], ref[1], dist[2], ref[2]);
   if (dist[0] >= INF)
     return RTB_REF_NONE;
-  if (dist[3] < INF) { stack.put(sp, make_int2(ref[3], __float_as_int(dist[3]))); sp++; }
-  if (dist[2] < INF) { stack.put(sp, make_int2(ref[2], __float_as_int(dist[2]))); sp++; }
-  if (dist[1] < INF) { stack.put(sp, make_int2(ref[1], __float_as_int(dist[1]))); sp++; }
+  if (dist[3] < INF) stack.push(make_int2(ref[3], __float_as_int(dist[3])));
+  if (dist[2] < INF) stack.push(make_int2(ref[2], __float_as_int(dist[2])));
+  if (dist[1] < INF) stack.push(make_int2(ref[1], __float_as_int(dist[1])));
   return ref[0];
 }
 
 /* WIDE: 0 = BvhNode (two children, 64 B), 1 = Bvh4Node (128 B), 2 = Bvh4QNode (compressed, 64 B) */
-template <int SD, int WIDE>
-__device__ __forceinline__ int node_step_w(const SceneView &sv, const RayF &rf, int cur, const WalkStack<SD> &stack, int &sp)
+template <int WIDE, class STK>
+__device__ __forceinline__ int node_step_w(const SceneView &sv, const RayF &rf, int cur, STK &stack)
 {
   if (WIDE == 2)
-    return node_step4q(sv, rf, cur, stack, sp);
+    return node_step4q(sv, rf, cur, stack);
   if (WIDE == 1)
-    return node_step4(sv, rf, cur, stack, sp);
-  return node_step(sv, rf, cur, stack, sp);
-}
-
-/* pop the next subtree that can still contain a nearer hit; RTB_REF_NONE when done */
-template <int SD>
-__device__ __forceinline__ int stack_pop(const RayF &rf, const WalkStack<SD> &stack, int &sp)
-{
-  while (sp > 0)
-  {
-    sp--;
-    int2 e = stack.get(sp);
-    if (__int_as_float(e.y) <= rf.tmax)
-      return e.x;
-  }
-  return RTB_REF_NONE;
+    return node_step4(sv, rf, cur, stack);
+  return node_step(sv, rf, cur, stack);
 }
 
 template <bool STATS, bool FILTER>
@@ -531,14 +537,14 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
   {
     int2 stack_mem[RTB_STACK_SIZE];
     WalkStack<0> stack = { nullptr, stack_mem, 0 };
-    int sp = 0;
+    stack.reset();
     int cur = sv.root_ref;
     while (cur != RTB_REF_NONE)
     {
       if (cur >= 0)
       {
         if (STATS) st.node_visits++;
-        cur = node_step(sv, rf, cur, stack, sp);
+        cur = node_step(sv, rf, cur, stack);
         if (cur != RTB_REF_NONE)
           continue;
       }
@@ -551,7 +557,7 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
                              rf.dfy, rf.dfz, rf.o_abs1, best, exact);
         rayf_update_tmax(rf, best);
       }
-      cur = stack_pop(rf, stack, sp);
+      cur = stack.pop(rf);
     }
   }
   if (STATS) st.prim_tests += exact;
@@ -649,15 +655,15 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
   {
     int2 stack_mem[RTB_STACK_SIZE - SD];
     WalkStack<SD> stack = { smem_column, stack_mem, smem_stride };
-    int sp = 0;
+    stack.reset();
     int cur = sv.root_ref;
     while (cur != RTB_REF_NONE)
     {
       while (cur >= 0 && cur != RTB_REF_NONE)
       {
         if (STATS) st.node_visits++;
-        int nxt = node_step_w<SD, WIDE>(sv, rf, cur, stack, sp);
-        cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+        int nxt = node_step_w<WIDE>(sv, rf, cur, stack);
+        cur = (nxt != RTB_REF_NONE) ? nxt : stack.pop(rf);
       }
       if (cur == RTB_REF_NONE)
         break;
@@ -667,7 +673,7 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
         test_prim_filtered<false>(load_prim(sv.prims, first + k), first + k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx,
                                   rf.dfy, rf.dfz, rf.o_abs1, best, exact);
       rayf_update_tmax(rf, best);
-      cur = stack_pop(rf, stack, sp);
+      cur = stack.pop(rf);
     }
   }
   if (STATS) st.prim_tests += exact;

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ Re
   RayF rf;
   int2 stack_mem[RTB_STACK_SIZE];
   WalkStack<0> stack = { nullptr, stack_mem, 0 };
-  int sp = 0;
+  stack.reset();
   int cur = 0, prim_i = 0, prim_end = 0;
   bool big_phase = false;
   int mode = (s < s_end) ? MODE_SHADE : MODE_IDLE;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ Re
       mode = MODE_SHADE;
       return;
     }
-    sp = 0;
+    stack.reset();
     set_cur(A.sv.root_ref);
   };
   auto begin_ray = [&]() {
@@ -218,9 +218,9 @@ __global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ Re
         for (int it = 0; it < RTB_NODE_BURST && mode == MODE_NODE; it++)
         {
           if (STATS) ts.node_visits++;
-          int nxt = node_step(A.sv, rf, cur, stack, sp);
+          int nxt = node_step(A.sv, rf, cur, stack);
           if (nxt == RTB_REF_NONE)
-            nxt = stack_pop(rf, stack, sp);
+            nxt = stack.pop(rf);
           set_cur(nxt);
         }
       }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ Re
           else
           {
             rayf_update_tmax(rf, best);
-            set_cur(stack_pop(rf, stack, sp));
+            set_cur(stack.pop(rf));
           }
         }
       }
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
   rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
   int2 stack_mem[RTB_STACK_SIZE];
   WalkStack<0> stack = { nullptr, stack_mem, 0 };
-  int sp = 0;
+  stack.reset();
   int cur = RTB_REF_NONE;
   bool walking = false;
 
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
         big_list_select_test(A.sv, st.o, st.d, rf, best, ts.prim_tests);
         if (rayf_walk_setup(A.sv, st.o, st.d, best, rf))
         {
-          sp = 0;
+          stack.reset();
           cur = A.sv.root_ref;
           walking = cur != RTB_REF_NONE;
         }
@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
         if (at_node)
         {
           if (STATS) ts.node_visits++;
-          int nxt = node_step(A.sv, rf, cur, stack, sp);
-          cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+          int nxt = node_step(A.sv, rf, cur, stack);
+          cur = (nxt != RTB_REF_NONE) ? nxt : stack.pop(rf);
           if (cur == RTB_REF_NONE)
             walking = false;
         }
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
           if (STATS) ts.prim_tests++;
         }
         rayf_update_tmax(rf, best);
-        cur = stack_pop(rf, stack, sp);
+        cur = stack.pop(rf);
         if (cur == RTB_REF_NONE)
           walking = false;
       }
@@ -915,6 +915,54 @@ extern "C" int rtb_path_records(rtb_scene *scene, const double *camera12, const 
   RTB_CUDA(cudaMemcpy(dists, d_dists.p, sizeof(double) * nr, cudaMemcpyDeviceToHost));
   if (radiance)
     RTB_CUDA(cudaMemcpy(radiance, d_rad.p, sizeof(float) * 3 * n_px, cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}
+
+/* ---- L2 read-bandwidth probe: the denominator for the walk's algorithmic bytes (SURVEY 8d asks for
+ * a measured L2 peak; MEASURED_PEAKS.json only holds HBM and BF16) -------------------------------- */
+__global__ void __launch_bounds__(256) k_probe_l2(const uint4 *__restrict__ buf, size_t n_vec, int iters, unsigned *sink)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  for (int it = 0; it < iters; it++)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride)
+    {
+      const uint4 v = __ldcg(buf + i); /* cached in L2 only */
+      acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+    }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9E3779B9u)
+    *sink = 1u;
+}
+
+extern "C" int rtb_probe_l2_bandwidth(size_t bytes, int iters, int device, float *gb_per_s)
+{
+  if (!gb_per_s || bytes < 4096 || iters < 1)
+  {
+    rtb_set_error("rtb_probe_l2_bandwidth: bad argument");
+    return RTB_EINVAL;
+  }
+  RTB_CUDA(cudaSetDevice(device));
+  Dev<uint4> d_buf;
+  Dev<unsigned> d_sink;
+  const size_t n_vec = bytes / sizeof(uint4);
+  RTB_CUDA(cudaMalloc(&d_buf.p, n_vec * sizeof(uint4)));
+  RTB_CUDA(cudaMalloc(&d_sink.p, sizeof(unsigned)));
+  RTB_CUDA(cudaMemset(d_buf.p, 1, n_vec * sizeof(uint4)));
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaEvent_t e0, e1;
+  RTB_CUDA(cudaEventCreate(&e0));
+  RTB_CUDA(cudaEventCreate(&e1));
+  k_probe_l2<<<sm_count * 8, 256>>>(d_buf.p, n_vec, 2, d_sink.p); /* warm: pull the buffer into L2 */
+  RTB_CUDA(cudaEventRecord(e0));
+  k_probe_l2<<<sm_count * 8, 256>>>(d_buf.p, n_vec, iters, d_sink.p);
+  RTB_CUDA(cudaEventRecord(e1));
+  RTB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.0f;
+  RTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gb_per_s = (float)((double)n_vec * sizeof(uint4) * iters / (ms * 1e-3) / 1e9);
   return RTB_OK;
 }
 

@@ -264,7 +264,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
   best.t = DBL_MAX; best.gid = 0x7FFFFFFF; best.slot = 0;
   int2 stack_mem[RTB_STACK_SIZE - SD];
   WalkStack<SD> stack = { &s_stack[0][threadIdx.x], stack_mem, 128 };
-  int sp = 0;
+  stack.reset();
   int cur = RTB_REF_NONE;
   unsigned node_visits = 0, prim_tests = 0;
 
@@ -298,7 +298,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         rayf_basic(o_, d_, rf);
         if (rayf_walk_setup(sv, o_, d_, best, rf))
         {
-          sp = 0;
+          stack.reset();
           cur = sv.root_ref;
           active = cur != RTB_REF_NONE;
         }
@@ -329,8 +329,8 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         while (cur >= 0 && cur != RTB_REF_NONE)
         {
           if (STATS) node_visits++;
-          int nxt = node_step_w<SD, WIDE>(sv, rf, cur, stack, sp);
-          cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+          int nxt = node_step_w<WIDE>(sv, rf, cur, stack);
+          cur = (nxt != RTB_REF_NONE) ? nxt : stack.pop(rf);
         }
       }
       else
@@ -345,8 +345,8 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
           if (at_node)
           {
             if (STATS) node_visits++;
-            int nxt = node_step_w<SD, WIDE>(sv, rf, cur, stack, sp);
-            cur = (nxt != RTB_REF_NONE) ? nxt : stack_pop(rf, stack, sp);
+            int nxt = node_step_w<WIDE>(sv, rf, cur, stack);
+            cur = (nxt != RTB_REF_NONE) ? nxt : stack.pop(rf);
           }
           if (__popc(bnode) < node_exit)
             break;
@@ -366,7 +366,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
           test_prim(load_prim(sv.prims, first + k), first + k, o, d, best);
         if (STATS) prim_tests += (unsigned)count;
         rayf_update_tmax(rf, best);
-        cur = stack_pop(rf, stack, sp);
+        cur = stack.pop(rf);
       }
       if (active && cur == RTB_REF_NONE)
       {
