@@ -180,6 +180,13 @@ typedef struct
   Geometry geometry;
 } SceneObject;
 
+/* integrator: the reference compiles trace_path in and cast_ray out (raytracer.c:207-211) */
+enum
+{
+  RT_INTEGRATOR_PATH = 0,   /* trace_path, raytracer.c:482-554 */
+  RT_INTEGRATOR_WHITTED = 1 /* cast_ray, raytracer.c:556-641 */
+};
+
 /* dielectric estimator */
 enum
 {
@@ -196,6 +203,7 @@ typedef struct
   int dielectric_mode; /* RT_DIELECTRIC_* */
   int device;          /* CUDA device ordinal */
   float *accum_out;    /* optional HOST float[H*W*3] sum of samples (not the mean) */
+  int integrator;      /* RT_INTEGRATOR_*: upstream picks at compile time (`#if 1`, raytracer.c:207) */
 } RenderParams;
 
 void render_params_default(RenderParams *p);

@@ -15,6 +15,8 @@
  *   rtb_render             the whole of render() (raytracer.c:176-223), host buffers in/out
  *   rtb_trace_rays         intersect() for arbitrary rays (raytracer.c:393-464): parity probe
  *   rtb_path_records       per-path vertex records: parity probe for the 1-bounce check
+ *   rtb_cast_rays          cast_ray() for arbitrary rays (raytracer.c:556-641): parity probe of the
+ *                          Whitted integrator (rtb_render_desc.integrator = RTB_INTEGRATOR_WHITTED)
  *   rtb_philox4x32_10      random_double()'s replacement (raytracer.c:227): KAT probe
  *   rtb_probe_l2_bandwidth no reference counterpart: measures the L2 roofline denominator
  *
@@ -54,6 +56,9 @@ extern "C" {
 #define RTB_DIELECTRIC_STOCHASTIC 0
 #define RTB_DIELECTRIC_SPLIT 1
 
+#define RTB_INTEGRATOR_PATH 0
+#define RTB_INTEGRATOR_WHITTED 1
+
 typedef struct rtb_scene rtb_scene; /* opaque: device-resident SoA geometry, materials, BVH */
 
 typedef struct
@@ -70,7 +75,10 @@ typedef struct
                                    lanes (0 = default) */
   int planes;                   /* sample sub-ranges accumulated separately and summed in order (fixes the
                                    floating-point summation order); 0 = auto */
-  int reserved2;
+  int reserved2;                /* kernel 6 tuning: ray sorting mode (0 = off) */
+  int integrator;               /* RTB_INTEGRATOR_PATH: trace_path (raytracer.c:482-554, the upstream default);
+                                   RTB_INTEGRATOR_WHITTED: cast_ray (raytracer.c:556-641), max_depth <= 15 */
+  int reserved3;
 } rtb_render_desc;
 
 typedef struct
@@ -128,6 +136,11 @@ int rtb_path_records(rtb_scene *scene, const double *camera12, const rtb_render_
                      int n_vertices, int32_t *ids, double *points, double *normals, double *dists,
                      float *radiance);
 int rtb_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, size_t n, uint32_t *out4, int device);
+
+/* cast_ray() for arbitrary rays (raytracer.c:556-641): parity probe of the Whitted integrator.
+ * rgb: HOST double[3*n]; ray_counts (optional): cast_ray invocations per ray (ray_count, raytracer.c:558) */
+int rtb_cast_rays(rtb_scene *scene, const double *rays6, size_t n_rays, int max_depth, double *rgb,
+                  unsigned long long *ray_counts);
 
 /* measurement probe: read bandwidth of an L2-resident buffer of `bytes` (128-bit ld.global.cg from every SM,
  * `iters` passes), in GB/s -- the denominator bench.py uses for the walk's L1/L2-served algorithmic bytes */

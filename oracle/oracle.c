@@ -586,6 +586,75 @@ static vec3 trace(Tracer *T, Rng *g, const Ray *ray, int depth, uint32_t branch)
 
 /* ---- drivers -------------------------------------------------------------- */
 
+/* ---- Whitted integrator: cast_ray (raytracer.c:556-641), operation for operation -----------
+ * Differences from upstream, both forced by the mesh-capable scene: the nearest hit is
+ * nearest_hit() above (mesh-aware), and the material is SceneObject.material instead of the
+ * flat Object's colour/flags.  For sphere-only scenes this function is bit-identical to the
+ * reference's cast_ray (tests/test_oracle_vs_ref.py::test_cast_ray_bit_exact). */
+static vec3 cast(const Tracer *T, long long *rays, long long *tests, const Ray *ray, int depth)
+{
+  (*rays)++;
+  const vec3 background = BACKGROUND;
+  if (depth > T->max_depth)
+    return background;
+  Nearest hit = nearest_hit(ray, T->objects, T->n, tests);
+  if (!hit.found)
+    return background;
+
+  vec3 out_color = ZERO_VECTOR;
+  vec3 light_pos = { 2, 7, 2 };
+  vec3 light_color = { 1, 1, 1 };
+
+  Ray light_ray = { hit.point, vec3_normalize(vec3_sub(light_pos, hit.point)) };
+  /* intersect(&light_ray, ..., NULL): any primitive along the unbounded ray (raytracer.c:571) */
+  bool in_shadow = nearest_hit(&light_ray, T->objects, T->n, tests).found;
+
+  const Material *m = &T->objects[hit.object_id].material;
+  vec3 object_color = m->color;
+  uint flags = m->flags;
+
+  double ka = 0.25;
+  double kd = 0.5;
+  double ks = 0.8;
+  double alpha = 10.0;
+
+  if (flags & M_CHECKERED)
+    object_color = checker(object_color, hit.u, hit.v, 10);
+
+  vec3 ambient = vec3_scalar_mult(light_color, ka);
+  vec3 diffuse = vec3_scalar_mult(light_color, kd * MAX(0.0, vec3_dot(hit.normal, light_ray.direction)));
+  vec3 reflected = reflect_dir(light_ray.direction, hit.normal);
+  vec3 view_dir = vec3_normalize(vec3_sub(hit.point, ray->origin));
+  vec3 specular = vec3_scalar_mult(light_color, ks * pow(MAX(vec3_dot(view_dir, reflected), 0.0), alpha));
+
+  vec3 surface = vec3_mult(vec3_add(ambient, vec3_scalar_mult(vec3_add(specular, diffuse), in_shadow ? 0 : 1)),
+                           object_color);
+
+  vec3 reflection = ZERO_VECTOR, refraction = ZERO_VECTOR;
+  double kr = 0, kt = 0;
+
+  if (flags & M_REFLECTION)
+  {
+    kr = 1.0;
+    Ray r = { hit.point, vec3_normalize(reflect_dir(ray->direction, hit.normal)) };
+    reflection = cast(T, rays, tests, &r, depth + 1);
+  }
+  if (flags & M_REFRACTION)
+  {
+    double transparency = 0.5;
+    double facingratio = -vec3_dot(ray->direction, hit.normal);
+    double fresnel = mix(pow(1 - facingratio, 3), 1, 0.1);
+    kr = fresnel;
+    kt = (1 - fresnel) * transparency;
+    Ray r = { hit.point, vec3_normalize(refract_dir(ray->direction, hit.normal, 1.0)) };
+    refraction = cast(T, rays, tests, &r, depth + 1);
+  }
+
+  out_color = vec3_add(out_color, surface);
+  out_color = vec3_add(out_color, vec3_add(vec3_scalar_mult(reflection, kr), vec3_scalar_mult(refraction, kt)));
+  return out_color;
+}
+
 void oracle_params_default(OracleParams *p)
 {
   memset(p, 0, sizeof(*p));
@@ -642,7 +711,8 @@ void oracle_render_sum(double *sum_rgb, const SceneObject *objects, size_t n, co
         double u = (double)(x + j1) / ((double)width - 1.0);
         double v = (double)(y + j2) / ((double)height - 1.0);
         Ray ray = camera_ray(camera, u, v);
-        vec3 sample = trace(&T, &g, &ray, 0, 1u);
+        vec3 sample = p->integrator == ORACLE_INTEGRATOR_WHITTED ? cast(&T, &g.rays, &g.tests, &ray, 0)
+                                                                 : trace(&T, &g, &ray, 0, 1u);
         pixel = vec3_add(pixel, sample);
       }
       double *o = sum_rgb + 3 * ((size_t)y * width + x);
@@ -777,6 +847,29 @@ void oracle_path_records(const SceneObject *objects, size_t n, const Camera *cam
 
 /* jitter of (pixel, sample) under the keyed layout, for feeding the reference's
  * get_camera_ray with the very same (u,v) the GPU uses */
+/* cast_ray() for arbitrary rays: rgb[3*i..] and (optionally) the number of cast_ray calls per ray */
+void oracle_cast_rays(const SceneObject *objects, size_t n_obj, const double *rays, long long n_rays,
+                      int max_depth, double *rgb, long long *ray_counts, int threads)
+{
+  OracleParams p;
+  oracle_params_default(&p);
+  p.max_depth = max_depth;
+  if (threads < 1)
+    threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 64)
+  for (long long i = 0; i < n_rays; i++)
+  {
+    Tracer T;
+    tracer_setup(&T, objects, n_obj, &p);
+    Ray ray = { { rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2] }, { rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5] } };
+    long long nrays = 0, tests = 0;
+    vec3 c = cast(&T, &nrays, &tests, &ray, 0);
+    rgb[3 * i + 0] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+    if (ray_counts)
+      ray_counts[i] = nrays;
+  }
+}
+
 void oracle_keyed_jitter(uint64_t seed, uint32_t pixel, uint32_t sample, double *j2)
 {
   OracleParams p;

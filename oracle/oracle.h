@@ -12,6 +12,7 @@
 
 enum { ORACLE_RNG_LIBC = 0, ORACLE_RNG_STREAM = 1, ORACLE_RNG_PHILOX = 2 };
 enum { ORACLE_DIELECTRIC_STOCHASTIC = 0, ORACLE_DIELECTRIC_SPLIT = 1 };
+enum { ORACLE_INTEGRATOR_PATH = 0, ORACLE_INTEGRATOR_WHITTED = 1 };
 
 typedef struct
 {
@@ -21,7 +22,7 @@ typedef struct
   int sample_offset;   /* keyed RNG: global index of the first sample */
   uint64_t seed;       /* srand() seed (LIBC) or Philox key (PHILOX) */
   int threads;         /* OpenMP threads (keyed RNG only; LIBC is sequential) */
-  int reserved;
+  int integrator;      /* ORACLE_INTEGRATOR_*: trace_path (raytracer.c:482) or cast_ray (raytracer.c:556) */
 } OracleParams;
 
 void oracle_params_default(OracleParams *p);
@@ -54,5 +55,8 @@ long long oracle_trace_path_stream(const SceneObject *objects, size_t n_obj, con
 void oracle_path_records(const SceneObject *objects, size_t n, const Camera *camera, int width, int height,
                          int sample, int n_vertices, const OracleParams *p, int32_t *ids, double *points,
                          double *normals, double *dists, double *radiance);
+
+void oracle_cast_rays(const SceneObject *objects, size_t n_obj, const double *rays, long long n_rays,
+                      int max_depth, double *rgb, long long *ray_counts, int threads);
 
 #endif

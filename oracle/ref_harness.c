@@ -258,6 +258,24 @@ void ref_checkered(const double *color3, double u, double v, double M, double *o
   out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
 
+/* the reference's own cast_ray (raytracer.c:556-641; compiled out of its render() by `#if 1`) */
+void ref_cast_rays(Object *objects, size_t n_obj, const double *rays, long long n_rays, int max_depth,
+                   double *rgb, long long *ray_counts)
+{
+  int saved = g_ref_max_depth;
+  g_ref_max_depth = max_depth;
+  for (long long i = 0; i < n_rays; i++)
+  {
+    Ray ray = {{rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]}, {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]}};
+    long long before = ray_count;
+    vec3 c = cast_ray(&ray, objects, n_obj, 0);
+    rgb[3 * i + 0] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+    if (ray_counts)
+      ray_counts[i] = ray_count - before;
+  }
+  g_ref_max_depth = saved;
+}
+
 double ref_random_double_from(int32_t r31)
 {
   int32_t s[1] = {r31};

@@ -21,7 +21,7 @@ LIB_HOST = os.path.join(_HERE, "libraytracer_b200.so")
 RTB_SYMBOLS = [
     "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_scene_create_objects", "rtb_scene_create",
     "rtb_scene_info_get", "rtb_scene_destroy", "rtb_render_accum", "rtb_tonemap", "rtb_render",
-    "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth",
+    "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth", "rtb_cast_rays",
 ]
 # the reference's exported surface (raytracer.h:135-164) plus the documented extensions
 HOST_SYMBOLS = [
@@ -75,6 +75,7 @@ def _bind(cu, host):
     cu.rtb_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int] + [C.c_void_p] * 6
     cu.rtb_path_records.argtypes = [C.c_void_p, dp, C.POINTER(abi.RtbRenderDesc), C.c_int, C.c_int] + [C.c_void_p] * 5
     cu.rtb_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    cu.rtb_cast_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     cu.rtb_probe_l2_bandwidth.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]
 
     host.init_camera.argtypes = [C.POINTER(abi.Camera), abi.Vec3, abi.Vec3, C.POINTER(abi.Options)]
@@ -221,7 +222,7 @@ def render(objects, camera, width, height, samples):
 
 # ---- the C ABI ----------------------------------------------------------------------------
 
-def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0):
+def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0, integrator=0):
     d = abi.RtbRenderDesc()
     d.width, d.height = width, height
     d.sample_begin, d.sample_end = sample_begin, sample_end
@@ -232,6 +233,7 @@ def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCE
     d.reserved = tune
     d.planes = planes
     d.reserved2 = tune2
+    d.integrator = integrator
     return d
 
 
@@ -307,6 +309,17 @@ class Scene:
                                        out["prims"].ctypes.data, out["t"].ctypes.data, out["points"].ctypes.data,
                                        out["normals"].ctypes.data, out["uvs"].ctypes.data), "rtb_trace_rays")
         return out
+
+    def cast_rays(self, rays, max_depth=5):
+        """cast_ray() of the Whitted integrator (raytracer.c:556-641) for arbitrary rays ->
+        (rgb float64 [n, 3], cast_ray invocations per ray)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        n = len(rays)
+        rgb = np.zeros((n, 3), np.float64)
+        counts = np.zeros(n, np.uint64)
+        _check(self._cu.rtb_cast_rays(self._h, rays.ctypes.data, n, int(max_depth), rgb.ctypes.data,
+                                      counts.ctypes.data), "rtb_cast_rays")
+        return rgb, counts
 
     def path_records(self, camera, desc, sample, n_vertices=2):
         cam = camera.as_array()

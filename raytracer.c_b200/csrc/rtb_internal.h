@@ -84,6 +84,7 @@ struct SceneView
   const float4 *big;   /* 3 float4 per oversized primitive (tested for every ray) */
   const float4 *mats;  /* 2 float4 per object */
   const float2 *tex;   /* 3 float2 per BVH primitive (BVH order) or NULL */
+  const double *colors; /* 3 doubles per object: the unscaled material colour (Whitted integrator) */
   int n_prims, n_big, root_ref, n_objects;
   float guard_lo[3], guard_hi[3]; /* box rays are re-based into before FP32 traversal */
 };
@@ -96,6 +97,7 @@ struct rtb_scene
   float4 *d_nodes4 = nullptr, *d_nodes4q = nullptr;
   float4 *d_nodes = nullptr, *d_prims = nullptr, *d_big = nullptr, *d_mats = nullptr;
   float2 *d_tex = nullptr;
+  double *d_colors = nullptr;
   float *d_scratch = nullptr; /* split planes */
   size_t scratch_bytes = 0;
   void *d_wf = nullptr;       /* wavefront kernels: ray queues + accumulation planes (rtb_wavefront.cu) */

@@ -595,6 +595,11 @@ static int check_desc(const rtb_render_desc *d)
     rtb_set_error("rtb_render_desc.kernel: 0 auto, 1..5 megakernel variants, 6 wavefront");
     return RTB_EINVAL;
   }
+  if (d->integrator != RTB_INTEGRATOR_PATH && d->integrator != RTB_INTEGRATOR_WHITTED)
+  {
+    rtb_set_error("rtb_render_desc.integrator: RTB_INTEGRATOR_PATH or RTB_INTEGRATOR_WHITTED");
+    return RTB_EINVAL;
+  }
   if (d->dielectric_mode != RTB_DIELECTRIC_STOCHASTIC)
   {
     rtb_set_error("dielectric_mode: only RTB_DIELECTRIC_STOCHASTIC runs on the GPU");
@@ -688,7 +693,13 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   }
   else
   {
-    if (wavefront)
+    if (desc->integrator == RTB_INTEGRATOR_WHITTED)
+    {
+      int wrc = whitted_render(scene, A, d_accum, stream, launches);
+      if (wrc != RTB_OK)
+        return wrc;
+    }
+    else if (wavefront)
     {
       int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr, launches, counters ? phase_ms : nullptr);
       if (wrc != RTB_OK)

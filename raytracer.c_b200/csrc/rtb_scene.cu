@@ -546,6 +546,7 @@ struct HostScene
   std::vector<SphereIn> spheres;
   std::vector<MeshRange> meshes;
   std::vector<float4> mats; /* 2 per object */
+  std::vector<double> colors; /* 3 per object, unscaled (cast_ray reads objects[i].color, raytracer.c:575) */
   size_t n_objects = 0;
   long long n_prims = 0;
 };
@@ -605,6 +606,9 @@ void push_material(HostScene &hs, uint32_t flags, const RefVec3 &color, const Re
   memcpy(&m1.w, &flags, 4);
   hs.mats.push_back(m0);
   hs.mats.push_back(m1);
+  hs.colors.push_back(color.x);
+  hs.colors.push_back(color.y);
+  hs.colors.push_back(color.z);
 }
 
 int gather_scene_objects(const RefSceneObject *objs, size_t n, HostScene &hs)
@@ -741,6 +745,10 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   if (!hs.mats.empty())
     RTB_CUDA(cudaMemcpyAsync(sc->d_mats, hs.mats.data(), sizeof(float4) * hs.mats.size(), cudaMemcpyHostToDevice, 0));
   dev_bytes += sizeof(float4) * hs.mats.size();
+  RTB_CUDA(pool_alloc(&sc->d_colors, std::max<size_t>(3, hs.colors.size())));
+  if (!hs.colors.empty())
+    RTB_CUDA(cudaMemcpyAsync(sc->d_colors, hs.colors.data(), sizeof(double) * hs.colors.size(), cudaMemcpyHostToDevice, 0));
+  dev_bytes += sizeof(double) * hs.colors.size();
   RTB_CUDA(pool_alloc(&sc->d_counters, 8));
   /* 3 float4 per record, followed by 2 float4 per FP32 copy */
   RTB_CUDA(pool_alloc(&sc->d_big, 5 * std::max<size_t>(1, big_spheres.size())));
@@ -946,6 +954,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   view.prims = sc->d_prims;
   view.big = sc->d_big;
   view.mats = sc->d_mats;
+  view.colors = sc->d_colors;
   view.tex = sc->d_tex;
 
   sc->info.n_objects = hs.n_objects;
@@ -1021,7 +1030,7 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
   cudaSetDevice(scene->device);
   /* stream-ordered: the memory goes back to the pool once work queued before this point on
    * the legacy default stream (which synchronises with every blocking stream) is done */
-  void *bufs[] = { scene->d_nodes4q, scene->d_nodes4, scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_tex,
+  void *bufs[] = { scene->d_nodes4q, scene->d_nodes4, scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_colors, scene->d_tex,
                    scene->d_scratch, scene->d_counters, scene->d_wf };
   for (void *b : bufs)
     if (b)

@@ -9,9 +9,11 @@
  *   -S <seed>                Philox key (default 1666943821, main.c:182)
  *   -g <device>              CUDA device ordinal
  *   -c default|spheres:N|mesh:GRID|obj:FILE
+ *   -i path|whitted          integrator: trace_path (upstream default) or cast_ray (raytracer.c:207-211)
  * Deliberately NOT reproduced: the option parser's mis-parse of values whose second
  * character is h/w/s/o and the SIGINT handler's double free.
  */
+#include <string.h>
 #include <time.h>
 
 #include "raytracer.h"
@@ -22,7 +24,7 @@ int rt_write_png(const char *filename, int w, int h, int comp, const void *data,
 typedef struct
 {
   Options options;
-  int max_depth, device;
+  int max_depth, device, integrator;
   uint64_t seed;
   const char *scene;
 } Cli;
@@ -31,6 +33,7 @@ static void usage(const char *prog)
 {
   fprintf(stderr, "Usage: %s -w <width> -h <height> -s <samples per pixel> -o <filename>\n", prog);
   fprintf(stderr, "       [-d <max depth>] [-S <seed>] [-g <cuda device>] [-c default|spheres:N|mesh:GRID|obj:FILE]\n");
+  fprintf(stderr, "       [-i path|whitted]\n");
 }
 
 static bool parse_cli(int argc, char **argv, Cli *cli)
@@ -59,6 +62,7 @@ static bool parse_cli(int argc, char **argv, Cli *cli)
     case 'S': cli->seed = strtoull(val, NULL, 10); break;
     case 'g': cli->device = atoi(val); break;
     case 'c': cli->scene = val; break;
+    case 'i': cli->integrator = (strcmp(val, "whitted") == 0) ? RT_INTEGRATOR_WHITTED : RT_INTEGRATOR_PATH; break;
     default:
       fprintf(stderr, "unknown option '%s'\n", a);
       return false;
@@ -104,6 +108,7 @@ int main(int argc, char **argv)
   rp.max_depth = cli.max_depth;
   rp.seed = cli.seed;
   rp.device = cli.device;
+  rp.integrator = cli.integrator;
 
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);

@@ -143,6 +143,7 @@ void render_params_default(RenderParams *p)
   p->dielectric_mode = RT_DIELECTRIC_STOCHASTIC;
   p->device = 0;
   p->accum_out = NULL;
+  p->integrator = RT_INTEGRATOR_PATH;
 }
 
 static void die(const char *where)
@@ -171,6 +172,7 @@ static void render_on_scene(uint8_t *framebuffer, rtb_scene *scene, Camera *came
   desc.max_depth = p.max_depth;
   desc.dielectric_mode = RTB_DIELECTRIC_STOCHASTIC;
   desc.seed = p.seed;
+  desc.integrator = p.integrator == RT_INTEGRATOR_WHITTED ? RTB_INTEGRATOR_WHITTED : RTB_INTEGRATOR_PATH;
 
   const double *cam = (const double *)camera; /* 12 doubles, raytracer.h:121-124 */
   rtb_counters counters;

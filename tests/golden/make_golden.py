@@ -62,7 +62,23 @@ def path_cases(seed=103, n=200):
     return rays, streams
 
 
+def whitted_golden():
+    """cast_ray (raytracer.c:556-641) of the unmodified reference on fixed rays: the default scene
+    (checkered + mirror + dielectric spheres) and a packed sphere field with mixed materials"""
+    out = {}
+    rays = random_rays_in_room(np.random.default_rng(106), 3000)
+    objs = api.scene_default(320, 180)
+    out["c1_rgb"], out["c1_calls"] = ol.ref_cast_rays(objs, rays, max_depth=5)
+    field = api.scene_sphere_field(400, 96, 54, mix=(0.3, 0.3, 0.3))
+    out["field_rgb"], out["field_calls"] = ol.ref_cast_rays(field, rays, max_depth=8)
+    np.savez_compressed(os.path.join(HERE, "whitted.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "whitted":
+        whitted_golden()
+        return
+    whitted_golden()
     ref = ol.ref()
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
 

@@ -24,11 +24,12 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref.so")
 
 RNG = {"libc": 0, "stream": 1, "philox": 2}
 DIELECTRIC = {"stochastic": 0, "split": 1}
+INTEGRATOR = {"path": 0, "whitted": 1}
 
 
 class OracleParams(C.Structure):
     _fields_ = [("max_depth", C.c_int), ("rng_mode", C.c_int), ("dielectric_mode", C.c_int),
-                ("sample_offset", C.c_int), ("seed", C.c_uint64), ("threads", C.c_int), ("reserved", C.c_int)]
+                ("sample_offset", C.c_int), ("seed", C.c_uint64), ("threads", C.c_int), ("integrator", C.c_int)]
 
 
 _oracle = None
@@ -77,7 +78,8 @@ def ref():
     return _ref
 
 
-def params(rng="libc", dielectric="split", max_depth=5, seed=abi.SCENE_SEED, sample_offset=0, threads=None):
+def params(rng="libc", dielectric="split", max_depth=5, seed=abi.SCENE_SEED, sample_offset=0, threads=None,
+           integrator="path"):
     p = OracleParams()
     p.max_depth = max_depth
     p.rng_mode = RNG[rng]
@@ -85,6 +87,7 @@ def params(rng="libc", dielectric="split", max_depth=5, seed=abi.SCENE_SEED, sam
     p.sample_offset = sample_offset
     p.seed = seed
     p.threads = threads if threads is not None else (os.cpu_count() or 1)
+    p.integrator = INTEGRATOR[integrator]
     return p
 
 
@@ -115,12 +118,12 @@ def camera_ray(cam, u, v):
 
 
 def render_sum(scene, cam, width, height, samples, rng="philox", dielectric="stochastic", max_depth=5,
-               seed=abi.SCENE_SEED, sample_offset=0, threads=None):
+               seed=abi.SCENE_SEED, sample_offset=0, threads=None, integrator="path"):
     """per-pixel SUM over samples, float64 [H,W,3]; returns (sum, (rays, prim_tests))"""
     h = _holder(scene)
     out = np.zeros((height, width, 3), dtype=np.float64)
     ctr = (C.c_longlong * 2)()
-    p = params(rng, dielectric, max_depth, seed, sample_offset, threads)
+    p = params(rng, dielectric, max_depth, seed, sample_offset, threads, integrator)
     oracle().oracle_render_sum(_dptr(out), h.objects, C.c_size_t(h.n), C.byref(cam), width, height, samples,
                                C.byref(p), ctr)
     return out, (ctr[0], ctr[1])
@@ -150,6 +153,18 @@ def intersect_rays(scene, rays, threads=None):
                                    _dptr(out["normals"]), _dptr(out["uvs"]),
                                    threads if threads is not None else (os.cpu_count() or 1))
     return out
+
+
+def cast_rays(scene, rays, max_depth=5, threads=None):
+    """the restated cast_ray (raytracer.c:556-641) -> (rgb [n,3], cast_ray calls per ray)"""
+    h = _holder(scene)
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+    n = len(rays)
+    rgb = np.zeros((n, 3))
+    counts = np.zeros(n, np.int64)
+    oracle().oracle_cast_rays(h.objects, C.c_size_t(h.n), _dptr(rays), C.c_longlong(n), int(max_depth), _dptr(rgb),
+                              _dptr(counts), threads if threads is not None else (os.cpu_count() or 1))
+    return rgb, counts
 
 
 def trace_path_stream(scene, ray6, stream, depth=0, dielectric="split", max_depth=5):
@@ -234,6 +249,18 @@ def ref_intersect_rays(objs, rays):
     ref().ref_intersect_rays(_dptr(arr), C.c_size_t(len(arr)), _dptr(rays), C.c_longlong(n), _dptr(out["ids"]),
                              _dptr(out["points"]), _dptr(out["normals"]), _dptr(out["uvs"]), _dptr(out["last_t"]))
     return out
+
+
+def ref_cast_rays(objs, rays, max_depth=5):
+    """the reference's own cast_ray for arbitrary rays -> (rgb [n,3], cast_ray calls per ray)"""
+    arr = np.ascontiguousarray(objs, dtype=abi.OBJECT_DTYPE)
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+    n = len(rays)
+    rgb = np.zeros((n, 3))
+    counts = np.zeros(n, np.int64)
+    ref().ref_cast_rays(_dptr(arr), C.c_size_t(len(arr)), _dptr(rays), C.c_longlong(n), int(max_depth), _dptr(rgb),
+                        _dptr(counts))
+    return rgb, counts
 
 
 def ref_trace_path_stream(objs, ray6, stream, depth=0, max_depth=5):

@@ -103,3 +103,17 @@ def test_golden_converged_noise_floor(ol, api):
     lo = ol.tonemap(g["mean_quarter"].astype(np.float64), 1)
     p = psnr_u8(hi, lo)
     assert 28.0 < p < 50.0, p  # 1024 spp vs 2048 spp ~ 33 dB at 320x180
+
+
+def test_oracle_cast_ray_matches_the_reference_golden(ol, api):
+    """Whitted integrator: the restated cast_ray against the reference's own cast_ray outputs
+    (tests/golden/whitted.npz, made by make_golden.py from oracle/_ref): bit-identical colours
+    and identical cast_ray call counts"""
+    g = np.load(os.path.join(GOLD, "whitted.npz"))
+    rays = random_rays_in_room(np.random.default_rng(106), 3000)
+    rgb, calls = ol.cast_rays(api.scene_default(320, 180), rays, max_depth=5)
+    assert np.array_equal(rgb, g["c1_rgb"]) and np.array_equal(calls, g["c1_calls"])
+    field = api.scene_sphere_field(400, 96, 54, mix=(0.3, 0.3, 0.3))
+    rgb, calls = ol.cast_rays(field, rays, max_depth=8)
+    assert np.array_equal(rgb, g["field_rgb"]) and np.array_equal(calls, g["field_calls"])
+    assert calls.max() > 4 and (g["c1_rgb"] != g["c1_rgb"][0]).any()

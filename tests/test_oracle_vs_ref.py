@@ -244,3 +244,16 @@ def test_stochastic_dielectric_has_the_split_expectation(R, api):
     # per-pixel: no systematic bias (mean signed relative difference near 0)
     rel = (b - a) / (0.5 * (a + b) + 1e-3)
     assert abs(rel.mean()) < 0.03
+
+
+def test_cast_ray_bit_exact(ref_or_skip, api):
+    """Whitted integrator: the restated cast_ray vs the reference's own cast_ray
+    (raytracer.c:556-641) -- colours bit-identical, ray_count identical, depths 0..8"""
+    ol = ref_or_skip
+    rays = random_rays_in_room(np.random.default_rng(31), 1500)
+    for objs, depth in ((api.scene_default(320, 180), 5), (api.scene_default(640, 380), 0),
+                        (api.scene_sphere_field(300, 96, 54, mix=(0.2, 0.4, 0.3)), 8)):
+        a, ca = ol.cast_rays(objs, rays, max_depth=depth)
+        b, cb = ol.ref_cast_rays(objs, rays, max_depth=depth)
+        assert np.array_equal(a, b) and np.array_equal(ca, cb)
+    assert ca.max() > 3  # chains of mirror / dielectric bounces are exercised
