@@ -129,24 +129,7 @@ def main():
         frames[f"ctr_{W}x{H}_s{S}_d{depth}"] = np.array(ctr, dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "c1_frames.npz"), **frames)
 
-    # a converged reference render for the PSNR gate: 96x54, 4096 spp (double means)
-    W, H, S = 96, 54, 4096
-    o = api.scene_default(W, H)
-    c = ol.ref_init_camera(W, H)
-    mean, ctr = ol.ref_render_mean(o, c, W, H, S, max_depth=5)
-    # and a second, independent seed at 1/4 of the samples: the reference's own noise floor
-    mean_b, _ = ol.ref_render_mean(o, c, W, H, S // 4, seed=7, max_depth=5)
-    np.savez_compressed(os.path.join(HERE, "c1_converged_96x54.npz"), mean=mean.astype(np.float32),
-                        mean_quarter=mean_b.astype(np.float32), spp=np.array([S, S // 4]), rays=np.array(ctr[0]))
-    # dielectric + mirror scene (the reference SPLITS at dielectrics, raytracer.c:522-529):
-    # converged means for the stochastic-estimator PSNR gate
-    W, H, S = 64, 36, 2048
-    o = api.scene_sphere_field(60, W, H, mix=(0.3, 0.4, 0.2))
-    c = ol.ref_init_camera(W, H)
-    mean, ctr = ol.ref_render_mean(o, c, W, H, S, max_depth=5)
-    mean_b, _ = ol.ref_render_mean(o, c, W, H, S // 4, seed=7, max_depth=5)
-    np.savez_compressed(os.path.join(HERE, "dielectric_converged_64x36.npz"), mean=mean.astype(np.float32),
-                        mean_quarter=mean_b.astype(np.float32), spp=np.array([S, S // 4]), rays=np.array(ctr[0]))
+    # the converged reference renders for the PSNR gate are made by make_converged.py (one process per seed)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

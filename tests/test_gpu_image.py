@@ -6,8 +6,10 @@ golden means (tests/golden/*_converged_*.npz: the UNMODIFIED reference's trace_p
 libc rand(), double precision, dielectrics SPLIT as upstream).  PSNR is taken on the 8-bit
 frames after the reference's own transfer (mean, gamma 5.0, truncation; raytracer.c:215-220).
 
+The reference renders are 32 768 spp (C1) and 16 384 spp (dielectric scene): 8 independent
+srand() seeds, one single-threaded reference process each (tests/golden/make_converged.py).
 The noise floor is measured, not assumed: the golden file also holds an independent
-reference render (other seed) at a quarter of the samples; PSNR(ref_quarter, ref_full) is
+reference render (other seeds) at a quarter of the samples; PSNR(ref_quarter, ref_full) is
 what the reference achieves against itself.  The GPU frame, rendered with 4x the full
 sample count, must do at least as well as that (+1 dB: it carries less noise than the
 quarter render) or reach 40 dB.
@@ -43,7 +45,7 @@ def _gate(gpu_api, ol, objs, W, H, gold_file, gpu_spp, max_depth=5):
 def test_psnr_default_scene(gpu_api, ol):
     W, H = 96, 54
     objs = gpu_api.scene_default(W, H)
-    got, floor, bias = _gate(gpu_api, ol, objs, W, H, "c1_converged_96x54.npz", gpu_spp=16384)
+    got, floor, bias = _gate(gpu_api, ol, objs, W, H, "c1_converged_96x54.npz", gpu_spp=131072)
     assert got >= min(40.0, floor + 1.0), (got, floor)
     assert abs(bias) < 0.01, "frame-average radiance must agree to 1% (unbiased estimator)"
 
@@ -53,7 +55,7 @@ def test_psnr_dielectric_scene_stochastic_vs_split(gpu_api, ol):
     expectation, so the converged frames agree at the noise floor"""
     W, H = 64, 36
     objs = gpu_api.scene_sphere_field(60, W, H, mix=(0.3, 0.4, 0.2))
-    got, floor, bias = _gate(gpu_api, ol, objs, W, H, "dielectric_converged_64x36.npz", gpu_spp=16384)
+    got, floor, bias = _gate(gpu_api, ol, objs, W, H, "dielectric_converged_64x36.npz", gpu_spp=65536)
     assert got >= min(40.0, floor + 1.0), (got, floor)
     assert abs(bias) < 0.01
 
