@@ -78,7 +78,8 @@ typedef struct
   int reserved2;                /* kernel 6 tuning: ray sorting mode (0 = off) */
   int integrator;               /* RTB_INTEGRATOR_PATH: trace_path (raytracer.c:482-554, the upstream default);
                                    RTB_INTEGRATOR_WHITTED: cast_ray (raytracer.c:556-641), max_depth <= 15 */
-  int reserved3;
+  int profile;                  /* with `counters`: 1 = also count BVH node visits and time the wavefront kernels
+                                   with CUDA events (trace_ms, shade_ms); 0 = rays, primitive tests and paths only */
 } rtb_render_desc;
 
 typedef struct
@@ -115,6 +116,10 @@ int rtb_scene_create_objects(const void *objects88, size_t n_objects, int device
 int rtb_scene_create(const void *scene_objects96, size_t n_objects, int device, rtb_scene **out);
 int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info);
 void rtb_scene_destroy(rtb_scene *scene);
+
+/* The wavefront kernels' workspace (ray queues, up to 11.7 GB) is parked per device when a scene is
+ * destroyed and reused by the next scene; this returns the parked buffer of `device` to the driver. */
+void rtb_release_workspace(int device);
 
 /* d_accum: DEVICE float[height*width*3], OVERWRITTEN with the sum over the call's samples.
  * Asynchronous on `stream` unless `counters` is non-NULL (then it synchronises to read them). */

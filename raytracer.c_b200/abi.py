@@ -90,7 +90,7 @@ class RtbRenderDesc(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("sample_begin", C.c_int),
                 ("sample_end", C.c_int), ("max_depth", C.c_int), ("dielectric_mode", C.c_int),
                 ("seed", C.c_uint64), ("kernel", C.c_int), ("reserved", C.c_int),
-                ("planes", C.c_int), ("reserved2", C.c_int), ("integrator", C.c_int), ("reserved3", C.c_int)]
+                ("planes", C.c_int), ("reserved2", C.c_int), ("integrator", C.c_int), ("profile", C.c_int)]
 
 
 class RtbCounters(C.Structure):

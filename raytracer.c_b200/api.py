@@ -20,7 +20,7 @@ LIB_HOST = os.path.join(_HERE, "libraytracer_b200.so")
 # every symbol include/rtb200.h declares
 RTB_SYMBOLS = [
     "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_scene_create_objects", "rtb_scene_create",
-    "rtb_scene_info_get", "rtb_scene_destroy", "rtb_render_accum", "rtb_tonemap", "rtb_render",
+    "rtb_scene_info_get", "rtb_scene_destroy", "rtb_release_workspace", "rtb_render_accum", "rtb_tonemap", "rtb_render",
     "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth", "rtb_cast_rays",
 ]
 # the reference's exported surface (raytracer.h:135-164) plus the documented extensions
@@ -222,7 +222,7 @@ def render(objects, camera, width, height, samples):
 
 # ---- the C ABI ----------------------------------------------------------------------------
 
-def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0, integrator=0):
+def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0, integrator=0, profile=1):
     d = abi.RtbRenderDesc()
     d.width, d.height = width, height
     d.sample_begin, d.sample_end = sample_begin, sample_end
@@ -234,6 +234,7 @@ def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCE
     d.planes = planes
     d.reserved2 = tune2
     d.integrator = integrator
+    d.profile = profile
     return d
 
 

@@ -106,6 +106,14 @@ struct rtb_scene
   rtb_scene_info info{};
 };
 
+/* Wavefront workspace (ray queues + planes, up to 11.7 GB): owned by a scene while it renders,
+ * parked per device when the scene is destroyed and handed to the next scene that needs one.
+ * render() creates and destroys a scene per call; going through the memory pool for a buffer of
+ * this size made the call time erratic (the freed block gets carved up by the next scene's small
+ * allocations, and a fresh 11.7 GB allocation costs ~1.5 s on this platform). */
+void *rtb_workspace_take(int device, size_t need, size_t *bytes); /* NULL if none parked or too small */
+void rtb_workspace_park(int device, void *p, size_t bytes);       /* device must be idle w.r.t. p */
+
 /* error plumbing */
 void rtb_set_error(const std::string &msg);
 #define RTB_CUDA(call)                                                                         \

@@ -701,7 +701,8 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     }
     else if (wavefront)
     {
-      int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr, launches, counters ? phase_ms : nullptr);
+      int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr && desc->profile != 0, launches,
+                          (counters && desc->profile != 0) ? phase_ms : nullptr);
       if (wrc != RTB_OK)
         return wrc;
     }

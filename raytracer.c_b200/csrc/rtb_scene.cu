@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 /* ---- error text ------------------------------------------------------------- */
@@ -1023,15 +1024,72 @@ extern "C" int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info)
   return RTB_OK;
 }
 
+namespace
+{
+struct ParkedWorkspace { void *p = nullptr; size_t bytes = 0; };
+std::mutex g_workspace_mutex;
+ParkedWorkspace g_workspace[64];
+}
+
+void *rtb_workspace_take(int device, size_t need, size_t *bytes)
+{
+  if (device < 0 || device >= 64)
+    return nullptr;
+  std::lock_guard<std::mutex> lock(g_workspace_mutex);
+  ParkedWorkspace &w = g_workspace[device];
+  if (!w.p || w.bytes < need)
+    return nullptr;
+  void *p = w.p;
+  *bytes = w.bytes;
+  w.p = nullptr;
+  w.bytes = 0;
+  return p;
+}
+
+void rtb_workspace_park(int device, void *p, size_t bytes)
+{
+  if (!p)
+    return;
+  void *drop = p;
+  if (device >= 0 && device < 64)
+  {
+    std::lock_guard<std::mutex> lock(g_workspace_mutex);
+    ParkedWorkspace &w = g_workspace[device];
+    if (!w.p || w.bytes < bytes)
+    {
+      drop = w.p; /* keep the larger one */
+      w.p = p;
+      w.bytes = bytes;
+    }
+  }
+  if (drop)
+    cudaFree(drop);
+}
+
+extern "C" void rtb_release_workspace(int device)
+{
+  size_t bytes = 0;
+  cudaSetDevice(device);
+  if (void *p = rtb_workspace_take(device, 0, &bytes))
+    cudaFree(p);
+}
+
 extern "C" void rtb_scene_destroy(rtb_scene *scene)
 {
   if (!scene)
     return;
   cudaSetDevice(scene->device);
+  if (scene->d_wf)
+  {
+    /* nothing may still be reading the queues when the next scene takes them over */
+    cudaDeviceSynchronize();
+    rtb_workspace_park(scene->device, scene->d_wf, scene->wf_bytes);
+    scene->d_wf = nullptr;
+  }
   /* stream-ordered: the memory goes back to the pool once work queued before this point on
    * the legacy default stream (which synchronises with every blocking stream) is done */
   void *bufs[] = { scene->d_nodes4q, scene->d_nodes4, scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_colors, scene->d_tex,
-                   scene->d_scratch, scene->d_counters, scene->d_wf };
+                   scene->d_scratch, scene->d_counters };
   for (void *b : bufs)
     if (b)
       cudaFreeAsync(b, 0);

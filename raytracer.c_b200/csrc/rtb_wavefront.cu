@@ -364,7 +364,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         const int first = code >> 3, count = (code & 7) + 1;
         for (int k = 0; k < count; k++)
           test_prim(load_prim(sv.prims, first + k), first + k, o, d, best);
-        if (STATS) prim_tests += (unsigned)count;
+        prim_tests += (unsigned)count;
         rayf_update_tmax(rf, best);
         cur = stack.pop(rf);
       }
@@ -384,8 +384,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
     }
   }
 
-  if (STATS)
-    wf_add_counters(totals, lane, 0ull, 0ull, prim_tests, node_visits, 0ull);
+  wf_add_counters(totals, lane, 0ull, 0ull, prim_tests, STATS ? node_visits : 0u, 0ull);
 }
 
 template <int V>
@@ -529,11 +528,23 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   if (scene->wf_bytes < need)
   {
     if (scene->d_wf)
-      RTB_CUDA(cudaFreeAsync(scene->d_wf, stream));
+    {
+      RTB_CUDA(cudaStreamSynchronize(stream)); /* an earlier call on this scene may still use it */
+      RTB_CUDA(cudaFree(scene->d_wf));
+    }
     scene->d_wf = nullptr;
     scene->wf_bytes = 0;
-    RTB_CUDA(cudaMallocAsync(&scene->d_wf, need, stream));
-    scene->wf_bytes = need;
+    size_t got = 0;
+    if (void *parked = rtb_workspace_take(scene->device, need, &got))
+    {
+      scene->d_wf = parked;
+      scene->wf_bytes = got;
+    }
+    else
+    {
+      RTB_CUDA(cudaMalloc(&scene->d_wf, need));
+      scene->wf_bytes = need;
+    }
   }
   char *p = static_cast<char *>(scene->d_wf);
   WfQueue q[2];
