@@ -53,12 +53,12 @@ struct PrimRec { float4 a, b, c; };
  * indexing the BVH-ordered primitive array. */
 struct BvhNode { float4 n0, n1, n2, n3; };
 
-/* BVH4 node, 128 bytes (four 256-bit loads): the BVH2 collapsed by two levels -- every inner
- * node at even depth absorbs its inner children.  Half the dependent fetches per ray.
+/* BVH4 node, 128 bytes (four 256-bit loads): the BVH2 collapsed greedily by surface area
+ * (k_emit4).  Half the dependent fetches per ray.
  *   q0 = lo.x of children 0..3, q1 = hi.x, q2 = lo.y, q3 = hi.y, q4 = lo.z, q5 = hi.z
  *   q6 = child references as int bits (same encoding as BvhNode; RTB_REF_NONE = empty slot)
  *   q7 = unused
- * Indexed like BvhNode by the Karras index of the inner node it was made from. */
+ * Dense, breadth-first; node 0 is the root. */
 struct Bvh4Node { float4 q[8]; };
 
 /* Compressed BVH4 node, 64 bytes (two 256-bit loads): child boxes quantised to 8 bits per

@@ -395,30 +395,90 @@ __global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restri
   atomicAdd(emitted, 1);
 }
 
-/* BVH4: one 128-byte node per inner node at EVEN depth whose subtree holds more than leaf_max
- * primitives; its inner children (odd depth) are absorbed, so it has 2..4 children */
+/* BVH4 by greedy collapse of the BVH2, one launch per BVH4 level.
+ * A work item is {BVH2 node that becomes a BVH4 node, index of that BVH4 node}.  The item starts
+ * with the node's two children and, while it has fewer than four, replaces the INNER child with
+ * the largest surface area by that child's two children (Wald et al. 2008).  Inner children get
+ * consecutive BVH4 indices from one atomicAdd (siblings are adjacent) and go to the next level's
+ * queue, so the node arrays are dense and in breadth-first order: the top of the tree is one
+ * contiguous block. */
+struct Emit4Queues
+{
+  int2 *items[2]; /* {bvh2 node, bvh4 index} */
+  int *counts;    /* [64 + 1] items per level */
+  int *n_nodes;   /* BVH4 nodes allocated so far */
+};
+
+__global__ void k_emit4_seed(Emit4Queues q)
+{
+  q.items[0][0] = make_int2(0, 0);
+  q.counts[0] = 1;
+  *q.n_nodes = 1;
+}
+
 __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restrict__ box_lo,
                         const float4 *__restrict__ box_hi, int n, const int2 *__restrict__ children,
                         const int *__restrict__ range_first, const float4 *__restrict__ node_lo,
-                        const float4 *__restrict__ node_hi, const int *__restrict__ parent_inner,
-                        const BuildParams *__restrict__ bp, float4 *__restrict__ out_nodes,
-                        float4 *__restrict__ out_nodes_q, int *__restrict__ emitted, int leaf_max)
+                        const float4 *__restrict__ node_hi, const BuildParams *__restrict__ bp,
+                        float4 *__restrict__ out_nodes, float4 *__restrict__ out_nodes_q, Emit4Queues q, int level,
+                        int leaf_max)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1)
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= q.counts[level])
     return;
-  if (__float_as_int(node_lo[i].w) <= leaf_max)
-    return;
-  int depth = 0;
-  for (int p = parent_inner[i]; p >= 0; p = parent_inner[p])
-    depth++;
-  if (depth & 1)
-    return;
+  const int2 work = q.items[level & 1][item];
+  const int i = work.y; /* index of the BVH4 node written here */
+
+  /* candidate children as BVH2 references: < 0 single primitive, >= 0 BVH2 inner node */
+  int cand[4];
+  int m = 2;
+  {
+    const int2 ch = children[work.x];
+    cand[0] = ch.x;
+    cand[1] = ch.y;
+  }
+  auto is_inner = [&](int c) { return c >= 0 && __float_as_int(node_lo[c].w) > leaf_max; };
+  auto area = [&](int c) {
+    const float4 a = node_lo[c], b = node_hi[c];
+    const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+    return dx * dy + dy * dz + dz * dx;
+  };
+  while (m < 4)
+  {
+    int pick = -1;
+    float best = -1.0f;
+    for (int k = 0; k < m; k++)
+      if (is_inner(cand[k]))
+      {
+        const float ar = area(cand[k]);
+        if (ar > best)
+        {
+          best = ar;
+          pick = k;
+        }
+      }
+    if (pick < 0)
+      break;
+    const int2 g = children[cand[pick]];
+    cand[pick] = g.x;
+    cand[m++] = g.y;
+  }
+  int n_inner = 0;
+  for (int k = 0; k < m; k++)
+    n_inner += is_inner(cand[k]) ? 1 : 0;
+  int child_index = 0, slot = 0;
+  if (n_inner > 0)
+  {
+    child_index = atomicAdd(q.n_nodes, n_inner);
+    slot = atomicAdd(&q.counts[level + 1], n_inner);
+  }
+
   const float pad = bp->pad;
   float lo[4][3], hi[4][3];
   int ref[4];
-  int m = 0;
-  auto add = [&](int c, bool may_be_inner) -> bool {
+  for (int k = 0; k < m; k++)
+  {
+    const int c = cand[k];
     float4 a, b;
     int r;
     if (c < 0)
@@ -433,26 +493,18 @@ __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restr
       int cc = __float_as_int(a.w);
       if (cc <= leaf_max)
         r = leaf_ref(range_first[c], cc);
-      else if (may_be_inner)
-        r = c;
       else
-        return false; /* inner child of the node itself: absorb */
+      {
+        r = child_index;
+        q.items[(level + 1) & 1][slot] = make_int2(c, child_index);
+        child_index++;
+        slot++;
+      }
     }
-    lo[m][0] = a.x - pad; lo[m][1] = a.y - pad; lo[m][2] = a.z - pad;
-    hi[m][0] = b.x + pad; hi[m][1] = b.y + pad; hi[m][2] = b.z + pad;
-    ref[m] = r;
-    m++;
-    return true;
-  };
-  const int2 ch = children[i];
-  const int c2[2] = { ch.x, ch.y };
-  for (int k = 0; k < 2; k++)
-    if (!add(c2[k], false))
-    {
-      const int2 g = children[c2[k]];
-      add(g.x, true);
-      add(g.y, true);
-    }
+    lo[k][0] = a.x - pad; lo[k][1] = a.y - pad; lo[k][2] = a.z - pad;
+    hi[k][0] = b.x + pad; hi[k][1] = b.y + pad; hi[k][2] = b.z + pad;
+    ref[k] = r;
+  }
   for (; m < 4; m++)
   {
     for (int a = 0; a < 3; a++) { lo[m][a] = 0.0f; hi[m][a] = 0.0f; }
@@ -510,7 +562,6 @@ __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restr
   oq[1] = o[6];
   oq[2] = make_float4(__uint_as_float(qlo[0]), __uint_as_float(qlo[1]), __uint_as_float(qlo[2]), __uint_as_float(qhi[0]));
   oq[3] = make_float4(__uint_as_float(qhi[1]), __uint_as_float(qhi[2]), 0.0f, 0.0f);
-  atomicAdd(emitted, 1);
 }
 
 __global__ void k_reorder(const unsigned *__restrict__ vals, int n, const PrimRec *__restrict__ in,
@@ -788,7 +839,9 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   DevBuf<unsigned long long> d_keys, d_keys_sorted;
   DevBuf<unsigned char> d_temp;
   DevBuf<int2> d_children;
-  DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc, d_misc4;
+  DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc, d_misc4, d_level_counts;
+  DevBuf<int2> d_items_a, d_items_b;
+  int h_levels[RTB_STACK_SIZE + 2] = { 0 };
   BuildParams h_bp;
   memset(&h_bp, 0, sizeof(h_bp));
   int h_misc[2] = { 0, 0 };
@@ -885,6 +938,10 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       RTB_CUDA(d_misc.alloc(2));
       RTB_CUDA(d_misc4.alloc(1));
       RTB_CUDA(cudaMemsetAsync(d_misc4.p, 0, sizeof(int), 0));
+      RTB_CUDA(d_items_a.alloc(N));
+      RTB_CUDA(d_items_b.alloc(N));
+      RTB_CUDA(d_level_counts.alloc(RTB_STACK_SIZE + 2));
+      RTB_CUDA(cudaMemsetAsync(d_level_counts.p, 0, sizeof(int) * (RTB_STACK_SIZE + 2), 0));
       RTB_CUDA(d_node_lo.alloc(N - 1));
       RTB_CUDA(d_node_hi.alloc(N - 1));
       RTB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * (N - 1), 0));
@@ -904,9 +961,21 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       RTB_CUDA(cudaGetLastError());
       RTB_CUDA(pool_alloc(&sc->d_nodes4, 8 * (N - 1)));
       RTB_CUDA(pool_alloc(&sc->d_nodes4q, 4 * (N - 1)));
-      k_emit4<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
-                             d_node_hi.p, d_parent_inner.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, d_misc4.p, leaf_max);
-      RTB_CUDA(cudaGetLastError());
+      {
+        Emit4Queues eq;
+        eq.items[0] = d_items_a.p;
+        eq.items[1] = d_items_b.p;
+        eq.counts = d_level_counts.p;
+        eq.n_nodes = d_misc4.p;
+        k_emit4_seed<<<1, 1>>>(eq);
+        /* a BVH4 level consumes at least one BVH2 level; an empty level costs an empty launch */
+        const int half_blocks = (int)((N / 2 + T) / T);
+        for (int level = 0; level < RTB_STACK_SIZE; level++)
+          k_emit4<<<half_blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
+                                      d_node_hi.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, eq, level, leaf_max);
+        RTB_CUDA(cudaGetLastError());
+        RTB_CUDA(cudaMemcpyAsync(h_levels, d_level_counts.p, sizeof(int) * (RTB_STACK_SIZE + 1), cudaMemcpyDeviceToHost, 0));
+      }
       k_reorder<<<blocks, T>>>(d_vals_sorted.p, (int)N, d_unsorted.p, reinterpret_cast<PrimRec *>(sc->d_prims),
                                want_tex ? d_tex_unsorted.p : nullptr, sc->d_tex);
       RTB_CUDA(cudaGetLastError());
@@ -942,7 +1011,11 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     }
     bvh_depth = h_misc[0];
     n_nodes = (size_t)h_misc[1];
-    if (bvh_depth > RTB_STACK_SIZE - 2)
+    int depth4 = 0;
+    while (depth4 < RTB_STACK_SIZE && h_levels[depth4] > 0)
+      depth4++;
+    /* the BVH2 walk pushes at most one entry per level, the BVH4 walk at most three */
+    if (bvh_depth > RTB_STACK_SIZE - 2 || 3 * depth4 > RTB_STACK_SIZE - 2)
     {
       rtb_set_error("BVH deeper than the traversal stack");
       return RTB_EINVAL;
