@@ -116,6 +116,38 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
     assert c2.node_visits == c0.node_visits and c2.prim_tests == c0.prim_tests  # same BVH2, same order
 
 
+def test_counters_without_profiling(gpu_api):
+    """rtb_render_desc.profile = 0 (what the drop-in render() uses): same sums, same ray and
+    primitive-test counts, no node-visit count, no per-kernel times"""
+    W, H = 64, 36
+    objs = gpu_api.scene_sphere_field(200, W, H, mix=(0.3, 0.3, 0.3))
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        _, a1, c1 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=6, profile=1), want_accum=True)
+        _, a0, c0 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=6, profile=0), want_accum=True)
+    assert np.array_equal(a0, a1)
+    assert c0.rays == c1.rays and c0.prim_tests == c1.prim_tests and c0.paths == c1.paths
+    assert c1.node_visits > 0 and c1.trace_ms > 0 and c1.trace_launches == 7
+    assert c0.node_visits == 0 and c0.trace_ms == 0
+
+
+def test_workspace_is_reused_across_scenes(gpu_api):
+    """render() creates and destroys a scene per call: the ray-queue workspace is parked per
+    device and taken over by the next scene (no growth of used device memory)"""
+    import torch
+    W, H = 128, 72
+    objs = gpu_api.scene_default(W, H)
+    cam = gpu_api.init_camera(W, H)
+    used = []
+    for _ in range(4):
+        with gpu_api.Scene(objs) as sc:
+            sc.render(cam, gpu_api.make_desc(W, H, 0, 8))
+        torch.cuda.synchronize()
+        free, total = torch.cuda.mem_get_info()
+        used.append(total - free)
+    assert max(used[1:]) - min(used[1:]) < (64 << 20), used
+
+
 def test_wavefront_depth_zero_and_empty(gpu_api):
     """max_depth 0 (one vertex per path) and an empty sample range"""
     W, H = 64, 36
