@@ -328,8 +328,11 @@ def main_gpu(args):
     e2e_step()  # warm
     sync_all()
     t0 = time.perf_counter()
+    e2e_calls = []
     for _ in range(e2e_steps):
+        tc = time.perf_counter()
         e2e_step()
+        e2e_calls.append((time.perf_counter() - tc) * 1e3)
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -378,7 +381,7 @@ def main_gpu(args):
                        "kernel": "wavefront (k_wf_generate / k_wf_trace / k_wf_shade), compressed BVH4"},
             "paths_per_s": paths_per_s, "rays_per_step": rays_step, "rays_per_path": rays_step / (world * W * H * spp),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": te[0].item(), "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(W * H * 3), "api": "render_scene()/render_ex() of libraytracer_b200.so" if world == 1
+                    "d2h_bytes_per_step": int(W * H * 3), "ms_per_call": [round(x, 2) for x in e2e_calls], "api": "render_scene()/render_ex() of libraytracer_b200.so" if world == 1
                     else "rtb_scene_create + rtb_render_accum + NCCL reduce + rtb_tonemap + D2H"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
