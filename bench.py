@@ -73,6 +73,14 @@ def build_host_scene(api, name, W, H, pinned=False):
     raise SystemExit(f"unknown workload {name}")
 
 
+def workload_config(name, spp, world):
+    W, H, _, depth, text = WORKLOADS[name]
+    return {"workload": f"{name}: {text}", "width": W, "height": H, "spp_per_gpu": spp, "max_depth": depth, "seed": SEED,
+            "l2": "512 MB memset between timed steps (L2 flushed)",
+            "parallelism": f"spp-sharded x{world}, one NCCL reduce",
+            "kernel": "wavefront (k_wf_generate / k_wf_trace / k_wf_shade), compressed BVH4"}
+
+
 def algorithmic_cost(name, n_prims, S, P):
     """per INTERSECTED ray.  flops = 2*L*22 + 4*P + 60, bytes = L*64 + 4*S,
     L = ceil(log2(N/4)); C1 is the brute-force case 38*20+60 flop, 38*16 B."""
@@ -196,7 +204,8 @@ def main_reference(args):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {text}", "sample": sample},
+        "config": dict(workload_config(args.workload, spp, args.gpus), sample=sample,
+                       note="the reference arm runs the bounded sample named in `sample` of this workload, on the host cores of rank 0"),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -375,10 +384,7 @@ def main_gpu(args):
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {text}", "width": W, "height": H, "spp_per_gpu": spp,
-                       "max_depth": depth, "seed": SEED, "l2": "512 MB memset between timed steps (L2 flushed)",
-                       "parallelism": f"spp-sharded x{world}, one NCCL reduce",
-                       "kernel": "wavefront (k_wf_generate / k_wf_trace / k_wf_shade), compressed BVH4"},
+            "config": workload_config(args.workload, spp, world),
             "paths_per_s": paths_per_s, "rays_per_step": rays_step, "rays_per_path": rays_step / (world * W * H * spp),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": te[0].item(), "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(W * H * 3), "ms_per_call": [round(x, 2) for x in e2e_calls], "api": "render_scene()/render_ex() of libraytracer_b200.so" if world == 1
