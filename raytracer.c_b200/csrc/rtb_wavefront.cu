@@ -184,10 +184,17 @@ __device__ __forceinline__ void wf_add_counters(unsigned long long *totals, int 
 
 /* ---- camera samples of one wave ------------------------------------------------------------
  * One thread per path slot; warps map to 8x4 pixel tiles of one plane so that the primary
- * rays a warp appends (and a trace warp later fetches together) are coherent. */
-__global__ void __launch_bounds__(128, 8) k_wf_generate(const __grid_constant__ RenderArgs A, int wave, WfQueue q,
-                                                     unsigned *count)
+ * rays a trace warp later fetches together are coherent.  The planes that still have a sample
+ * in this wave are a prefix [0, n_valid_planes), so the queue position of a ray is computed,
+ * not allocated: no atomics (one same-address atomic per warp made this kernel atomic-bound,
+ * 8 % of a step). */
+__global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ RenderArgs A, int wave, int n_valid_planes,
+                                                     WfQueue q, unsigned *count)
 {
+  __shared__ unsigned s_exact;
+  if (threadIdx.x == 0)
+    s_exact = 0u;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int tile = (int)(warp % A.n_tiles);
@@ -195,24 +202,42 @@ __global__ void __launch_bounds__(128, 8) k_wf_generate(const __grid_constant__ 
   const int x = (tile % A.tiles_x) * 8 + (lane & 7);
   const int y = (tile / A.tiles_x) * 4 + (lane >> 3);
   const int s = A.s_begin + plane * A.chunk + wave;
-  const bool valid = x < A.width && y < A.height && plane < A.splits && s < min(A.s_end, A.s_begin + (plane + 1) * A.chunk);
+  const bool valid = x < A.width && y < A.height && plane < n_valid_planes;
+  const unsigned n_px = (unsigned)(A.width * A.height);
   const unsigned pixel = (unsigned)(y * A.width + x);
+  const bool tiled = (A.width % 8) == 0 && (A.height % 4) == 0; /* every lane of every tile is a pixel */
 
-  PathState st;
-  st.o = d3_make(0, 0, 0);
-  st.d = d3_make(0, 0, 1);
-  st.tr = st.tg = st.tb = 1.0f;
-  HitRec seed;
-  seed.t = DBL_MAX; seed.gid = 0x7FFFFFFF; seed.slot = 0;
   unsigned exact = 0;
   if (valid)
   {
+    PathState st;
+    HitRec seed;
     path_begin(A, st, x, y, pixel, (unsigned)s);
     ray_seed_hit(A.sv, st.o, st.d, seed, exact);
+    const unsigned pid = (unsigned)plane * n_px + pixel;
+    const unsigned i = (unsigned)plane * n_px + (tiled ? (unsigned)tile * 32u + (unsigned)lane : pixel);
+    __stcs(q.o_xy + i, make_double2(st.o.x, st.o.y));
+    __stcs(q.oz_dx + i, make_double2(st.o.z, st.d.x));
+    __stcs(q.d_yz + i, make_double2(st.d.y, st.d.z));
+    __stcs(q.path + i, make_uint4(pid, __float_as_uint(st.tr), __float_as_uint(st.tg), __float_as_uint(st.tb)));
+    __stcs(q.hit + i, pack_hit(seed));
   }
-  const unsigned pid = (unsigned)plane * (unsigned)(A.width * A.height) + pixel;
-  wf_enqueue(q, count, valid, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed);
-  wf_add_counters(A.counters, lane, 0ull, 0ull, exact, 0ull, valid ? 1ull : 0ull);
+  for (int off = 16; off > 0; off >>= 1)
+    exact += __shfl_xor_sync(WF_FULL, exact, off);
+  if (lane == 0 && exact)
+    atomicAdd(&s_exact, exact);
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    if (s_exact)
+      atomicAdd(&A.counters[2], (unsigned long long)s_exact);
+    if (blockIdx.x == 0)
+    {
+      const unsigned n = (unsigned)n_valid_planes * n_px;
+      *count = n;
+      atomicAdd(&A.counters[4], (unsigned long long)n);
+    }
+  }
 }
 
 /* ---- nearest hit for a whole queue -----------------------------------------------------------
@@ -579,7 +604,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device);
   const int shade_blocks = sm_count * 16;
   const long long gen_warps = (long long)A.n_tiles * A.splits;
-  const int gen_blocks = (int)((gen_warps * 32 + 127) / 128);
+  const int gen_blocks = (int)((gen_warps * 32 + 255) / 256);
 
   /* per-kernel timing (only with counters): events around every trace launch */
   std::vector<cudaEvent_t> ev;
@@ -594,7 +619,10 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   for (int wave = 0; wave < A.chunk; wave++)
   {
     RTB_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), stream));
-    k_wf_generate<<<gen_blocks, 128, 0, stream>>>(A, wave, q[0], &counts[0]);
+    /* planes whose sub-range still has a sample number `wave`: all, or all but the (shorter) last */
+    const int last_len = (A.s_end - A.s_begin) - (A.splits - 1) * A.chunk;
+    const int n_valid_planes = wave < last_len ? A.splits : A.splits - 1;
+    k_wf_generate<<<gen_blocks, 256, 0, stream>>>(A, wave, n_valid_planes, q[0], &counts[0]);
     launches++;
     for (int b = 0; b < n_bounces; b++)
     {
