@@ -495,11 +495,11 @@ __global__ void k_trace_rays(const __grid_constant__ SceneView sv, const double 
   d3 d = d3_make(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
   HitRec best;
   TraceStats st = { 0u, 0u };
-  if (use_bvh == 5)
+  if (use_bvh == 5 && sv.nodes4q != nullptr)
     closest_hit_ww<false, 0, 2>(sv, o, d, best, st, nullptr, 0);
-  else if (use_bvh == 4)
+  else if (use_bvh == 4 && sv.nodes4 != nullptr)
     closest_hit_ww<false, 0, 1>(sv, o, d, best, st, nullptr, 0);
-  else if (use_bvh == 3)
+  else if (use_bvh >= 3)
     closest_hit_ww<false, 0>(sv, o, d, best, st, nullptr, 0);
   else if (use_bvh == 2)
     closest_hit<false, true>(sv, o, d, best, st);

@@ -845,6 +845,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   BuildParams h_bp;
   memset(&h_bp, 0, sizeof(h_bp));
   int h_misc[2] = { 0, 0 };
+  bool bvh4_ok = true;
 
   if (N > 0)
   {
@@ -1015,16 +1016,19 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     while (depth4 < RTB_STACK_SIZE && h_levels[depth4] > 0)
       depth4++;
     /* the BVH2 walk pushes at most one entry per level, the BVH4 walk at most three */
-    if (bvh_depth > RTB_STACK_SIZE - 2 || 3 * depth4 > RTB_STACK_SIZE - 2)
+    if (bvh_depth > RTB_STACK_SIZE - 2)
     {
       rtb_set_error("BVH deeper than the traversal stack");
       return RTB_EINVAL;
     }
+    /* a very unbalanced tree can be too deep for the BVH4 walk's stack while the BVH2 walk still
+     * fits: such a scene is rendered with the BVH2 walk (same results, see SceneView::nodes4q) */
+    bvh4_ok = 3 * depth4 <= RTB_STACK_SIZE - 2;
   }
 
   view.nodes = sc->d_nodes;
-  view.nodes4 = sc->d_nodes4;
-  view.nodes4q = sc->d_nodes4q;
+  view.nodes4 = bvh4_ok ? sc->d_nodes4 : nullptr;
+  view.nodes4q = bvh4_ok ? sc->d_nodes4q : nullptr;
   view.prims = sc->d_prims;
   view.big = sc->d_big;
   view.mats = sc->d_mats;

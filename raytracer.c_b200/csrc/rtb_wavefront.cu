@@ -534,6 +534,8 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   }
   if (node_exit == 0xFF)
     node_exit = 0; /* pure while-while */
+  if ((variant & (8 | 16)) != 0 && A.sv.nodes4q == nullptr && A.sv.root_ref >= 0 && A.sv.root_ref != RTB_REF_NONE)
+    variant = 6; /* the scene has no BVH4 (tree too deep for its stack): BVH2 walk */
   const int sort_mode = desc->reserved2 & 0xFF;
   const int sort_from = 1;                                           /* primary rays are coherent already */
   const int sort_until = (desc->reserved2 >> 8) & 0xFF ? (desc->reserved2 >> 8) & 0xFF : 255;

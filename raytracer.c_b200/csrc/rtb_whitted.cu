@@ -37,7 +37,10 @@ struct WhFrame
 __device__ __forceinline__ bool wh_nearest(const SceneView &sv, const d3 &o, const d3 &d, HitRec &best)
 {
   TraceStats ts = { 0u, 0u };
-  closest_hit_ww<false, 0, 2>(sv, o, d, best, ts, nullptr, 0);
+  if (sv.nodes4q != nullptr)
+    closest_hit_ww<false, 0, 2>(sv, o, d, best, ts, nullptr, 0);
+  else
+    closest_hit_ww<false, 0>(sv, o, d, best, ts, nullptr, 0); /* tree too deep for the BVH4 stack */
   return best.t < 1e300;
 }
 

@@ -296,3 +296,39 @@ def test_dropin_render_entry(gpu_api):
     with gpu_api.Scene(objs) as sc:
         fb_abi, _, _ = sc.render(cam, gpu_api.make_desc(W, H, 0, SPP, max_depth=5))
     assert np.array_equal(fb_host, fb_abi)
+
+
+def test_deep_unbalanced_tree(gpu_api, abi):
+    """spheres spaced geometrically along a line give a chain-like LBVH; if it is too deep for the
+    BVH4 walk's stack the scene falls back to the BVH2 walk -- either way the nearest hit equals
+    the brute-force loop and the wavefront sums equal the megakernel's"""
+    n = 58
+    objs = np.zeros(n, dtype=abi.OBJECT_DTYPE)
+    for k in range(n):
+        x = 30.0 * 0.62 ** k
+        objs[k]["flags"] = 2 if k % 3 else 4
+        objs[k]["radius"] = x * 0.2
+        objs[k]["center"] = (x, 0.3 * x, -5.0 + 0.1 * x)
+        objs[k]["color"] = (0.7, 0.6, 0.5)
+        objs[k]["emission"] = (0.5, 0.5, 0.5) if k % 5 == 0 else (0.0, 0.0, 0.0)
+    rng = np.random.default_rng(77)
+    o = rng.uniform(-2, 32, (4000, 3)) * np.array([1.0, 0.3, 0.05]) + np.array([0, 0, 10.0])
+    pick = rng.integers(0, n, 4000)
+    t = objs["center"][pick] + rng.normal(0.0, 0.6, (4000, 3)) * objs["radius"][pick][:, None]
+    d = t - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1)
+    W, H = 64, 36
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        info = sc.info
+        brute = sc.trace_rays(rays, use_bvh=0)
+        for mode in (1, 3, 4, 5):
+            got = sc.trace_rays(rays, use_bvh=mode)
+            for k in ("ids", "prims", "t", "points", "normals"):
+                assert np.array_equal(got[k], brute[k]), (mode, k)
+        _, a4, c4 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, kernel=4, planes=2), want_accum=True)
+        _, a6, c6 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, kernel=6, planes=2), want_accum=True)
+    print("bvh depth", info.bvh_depth, "hit fraction", (brute["ids"] >= 0).mean())
+    assert (brute["ids"] >= 0).mean() > 0.5 and info.bvh_depth >= 12
+    assert np.array_equal(a4, a6) and c4.rays == c6.rays
