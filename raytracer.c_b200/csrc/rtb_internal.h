@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "rtb200.h"
 
@@ -104,15 +106,18 @@ struct rtb_scene
   size_t wf_bytes = 0;
   unsigned long long *d_counters = nullptr;
   rtb_scene_info info{};
+  std::vector<std::pair<void *, size_t>> owned; /* every device buffer of the scene arrays, with its size */
 };
 
-/* Wavefront workspace (ray queues + planes, up to 11.7 GB): owned by a scene while it renders,
- * parked per device when the scene is destroyed and handed to the next scene that needs one.
- * render() creates and destroys a scene per call; going through the memory pool for a buffer of
- * this size made the call time erratic (the freed block gets carved up by the next scene's small
- * allocations, and a fresh 11.7 GB allocation costs ~1.5 s on this platform). */
-void *rtb_workspace_take(int device, size_t need, size_t *bytes); /* NULL if none parked or too small */
-void rtb_workspace_park(int device, void *p, size_t bytes);       /* device must be idle w.r.t. p */
+/* Per-device cache of device buffers.  render() creates and destroys a scene per call; sending
+ * ~13 buffers (0.3 GB of scene arrays, up to 11.7 GB of ray queues) through the CUDA memory pool
+ * on every call made the call time erratic: the pool re-grows whenever its free blocks get carved
+ * up differently, and a fresh allocation costs 0.1-1.5 s on this platform (measured:
+ * scene create 4 ms typically, 20-1500 ms on every third call).  A destroyed scene parks its
+ * buffers here; the next scene takes any parked buffer that fits (same shape -> exact matches,
+ * no allocation at all).  rtb_release_workspace() empties the cache. */
+void *rtb_cache_take(int device, size_t need, size_t *bytes); /* NULL if nothing parked fits */
+void rtb_cache_park(int device, void *p, size_t bytes);       /* the device must be done with p */
 
 /* error plumbing */
 void rtb_set_error(const std::string &msg);

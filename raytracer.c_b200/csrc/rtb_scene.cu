@@ -638,6 +638,24 @@ static cudaError_t pool_alloc(T **p, size_t n)
   return cudaMallocAsync(reinterpret_cast<void **>(p), sizeof(T) * (n ? n : 1), 0);
 }
 
+/* a buffer that lives as long as the scene: from the per-device cache if one fits, else from the pool */
+template <typename T>
+static cudaError_t scene_alloc(rtb_scene *sc, T **p, size_t n)
+{
+  const size_t need = sizeof(T) * (n ? n : 1);
+  size_t got = 0;
+  if (void *q = rtb_cache_take(sc->device, need, &got))
+  {
+    *p = static_cast<T *>(q);
+    sc->owned.emplace_back(q, got);
+    return cudaSuccess;
+  }
+  cudaError_t e = pool_alloc(p, n);
+  if (e == cudaSuccess)
+    sc->owned.emplace_back(static_cast<void *>(*p), need);
+  return e;
+}
+
 void push_material(HostScene &hs, uint32_t flags, const RefVec3 &color, const RefVec3 &emission)
 {
   /* Russian roulette (raytracer.c:497-502): survive iff u < prob with u = r31 / 2^31, i.e.
@@ -793,17 +811,17 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   size_t dev_bytes = 0;
 
   /* materials, counters, big list */
-  RTB_CUDA(pool_alloc(&sc->d_mats, std::max<size_t>(2, hs.mats.size())));
+  RTB_CUDA(scene_alloc(sc.get(), &sc->d_mats, std::max<size_t>(2, hs.mats.size())));
   if (!hs.mats.empty())
     RTB_CUDA(cudaMemcpyAsync(sc->d_mats, hs.mats.data(), sizeof(float4) * hs.mats.size(), cudaMemcpyHostToDevice, 0));
   dev_bytes += sizeof(float4) * hs.mats.size();
-  RTB_CUDA(pool_alloc(&sc->d_colors, std::max<size_t>(3, hs.colors.size())));
+  RTB_CUDA(scene_alloc(sc.get(), &sc->d_colors, std::max<size_t>(3, hs.colors.size())));
   if (!hs.colors.empty())
     RTB_CUDA(cudaMemcpyAsync(sc->d_colors, hs.colors.data(), sizeof(double) * hs.colors.size(), cudaMemcpyHostToDevice, 0));
   dev_bytes += sizeof(double) * hs.colors.size();
-  RTB_CUDA(pool_alloc(&sc->d_counters, 8));
+  RTB_CUDA(scene_alloc(sc.get(), &sc->d_counters, 8));
   /* 3 float4 per record, followed by 2 float4 per FP32 copy */
-  RTB_CUDA(pool_alloc(&sc->d_big, 5 * std::max<size_t>(1, big_spheres.size())));
+  RTB_CUDA(scene_alloc(sc.get(), &sc->d_big, 5 * std::max<size_t>(1, big_spheres.size())));
   DevBuf<SphereIn> d_big_in, d_bvh_in;
   if (!big_spheres.empty())
   {
@@ -903,9 +921,9 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     RTB_CUDA(cudaGetLastError());
     RTB_CUDA(cudaMemcpyAsync(&h_bp, d_bp.p, sizeof(h_bp), cudaMemcpyDeviceToHost, 0));
 
-    RTB_CUDA(pool_alloc(&sc->d_prims, 3 * N));
+    RTB_CUDA(scene_alloc(sc.get(), &sc->d_prims, 3 * N));
     if (want_tex)
-      RTB_CUDA(pool_alloc(&sc->d_tex, 3 * N));
+      RTB_CUDA(scene_alloc(sc.get(), &sc->d_tex, 3 * N));
 
     if ((int)N <= leaf_max)
     {
@@ -913,7 +931,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       RTB_CUDA(cudaMemcpyAsync(sc->d_prims, d_unsorted.p, sizeof(PrimRec) * N, cudaMemcpyDeviceToDevice, 0));
       if (want_tex)
         RTB_CUDA(cudaMemcpyAsync(sc->d_tex, d_tex_unsorted.p, sizeof(float2) * 3 * N, cudaMemcpyDeviceToDevice, 0));
-      RTB_CUDA(pool_alloc(&sc->d_nodes, 4));
+      RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes, 4));
       view.root_ref = ~(((0) << 3) | ((int)N - 1));
     }
     else
@@ -955,13 +973,13 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       k_depth<<<blocks, T>>>((int)N, d_parent_inner.p, d_parent_leaf.p, d_misc.p);
       RTB_CUDA(cudaGetLastError());
 
-      RTB_CUDA(pool_alloc(&sc->d_nodes, 4 * (N - 1)));
+      RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes, 4 * (N - 1)));
       RTB_CUDA(cudaMemsetAsync(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1), 0));
       k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
                             d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1, leaf_max);
       RTB_CUDA(cudaGetLastError());
-      RTB_CUDA(pool_alloc(&sc->d_nodes4, 8 * (N - 1)));
-      RTB_CUDA(pool_alloc(&sc->d_nodes4q, 4 * (N - 1)));
+      RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes4, 8 * (N - 1)));
+      RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes4q, 4 * (N - 1)));
       {
         Emit4Queues eq;
         eq.items[0] = d_items_a.p;
@@ -988,8 +1006,8 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   }
   else
   {
-    RTB_CUDA(pool_alloc(&sc->d_prims, 3));
-    RTB_CUDA(pool_alloc(&sc->d_nodes, 4));
+    RTB_CUDA(scene_alloc(sc.get(), &sc->d_prims, 3));
+    RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes, 4));
   }
   RTB_CUDA(cudaEventRecord(ev1, 0));
   RTB_CUDA(cudaEventSynchronize(ev1)); /* the only host wait of the build */
@@ -1103,40 +1121,49 @@ extern "C" int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info)
 
 namespace
 {
-struct ParkedWorkspace { void *p = nullptr; size_t bytes = 0; };
-std::mutex g_workspace_mutex;
-ParkedWorkspace g_workspace[64];
+struct ParkedBuffer { void *p; size_t bytes; };
+const size_t kCacheEntries = 24;
+std::mutex g_cache_mutex;
+std::vector<ParkedBuffer> g_cache[64];
 }
 
-void *rtb_workspace_take(int device, size_t need, size_t *bytes)
+void *rtb_cache_take(int device, size_t need, size_t *bytes)
 {
   if (device < 0 || device >= 64)
     return nullptr;
-  std::lock_guard<std::mutex> lock(g_workspace_mutex);
-  ParkedWorkspace &w = g_workspace[device];
-  if (!w.p || w.bytes < need)
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  std::vector<ParkedBuffer> &c = g_cache[device];
+  int pick = -1;
+  for (size_t k = 0; k < c.size(); k++)
+    if (c[k].bytes >= need && c[k].bytes <= need + need / 4 + 65536 && (pick < 0 || c[k].bytes < c[(size_t)pick].bytes))
+      pick = (int)k;
+  if (pick < 0)
     return nullptr;
-  void *p = w.p;
-  *bytes = w.bytes;
-  w.p = nullptr;
-  w.bytes = 0;
+  void *p = c[(size_t)pick].p;
+  *bytes = c[(size_t)pick].bytes;
+  c.erase(c.begin() + pick);
   return p;
 }
 
-void rtb_workspace_park(int device, void *p, size_t bytes)
+void rtb_cache_park(int device, void *p, size_t bytes)
 {
   if (!p)
     return;
   void *drop = p;
   if (device >= 0 && device < 64)
   {
-    std::lock_guard<std::mutex> lock(g_workspace_mutex);
-    ParkedWorkspace &w = g_workspace[device];
-    if (!w.p || w.bytes < bytes)
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    std::vector<ParkedBuffer> &c = g_cache[device];
+    c.push_back(ParkedBuffer{ p, bytes });
+    drop = nullptr;
+    if (c.size() > kCacheEntries)
     {
-      drop = w.p; /* keep the larger one */
-      w.p = p;
-      w.bytes = bytes;
+      size_t smallest = 0;
+      for (size_t k = 1; k < c.size(); k++)
+        if (c[k].bytes < c[smallest].bytes)
+          smallest = k;
+      drop = c[smallest].p;
+      c.erase(c.begin() + (long)smallest);
     }
   }
   if (drop)
@@ -1145,10 +1172,16 @@ void rtb_workspace_park(int device, void *p, size_t bytes)
 
 extern "C" void rtb_release_workspace(int device)
 {
-  size_t bytes = 0;
+  if (device < 0 || device >= 64)
+    return;
   cudaSetDevice(device);
-  if (void *p = rtb_workspace_take(device, 0, &bytes))
-    cudaFree(p);
+  std::vector<ParkedBuffer> drop;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    drop.swap(g_cache[device]);
+  }
+  for (const ParkedBuffer &b : drop)
+    cudaFree(b.p);
 }
 
 extern "C" void rtb_scene_destroy(rtb_scene *scene)
@@ -1156,19 +1189,13 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
   if (!scene)
     return;
   cudaSetDevice(scene->device);
+  /* nothing may still be using the buffers when the next scene takes them over */
+  cudaDeviceSynchronize();
+  for (const std::pair<void *, size_t> &b : scene->owned)
+    rtb_cache_park(scene->device, b.first, b.second);
   if (scene->d_wf)
-  {
-    /* nothing may still be reading the queues when the next scene takes them over */
-    cudaDeviceSynchronize();
-    rtb_workspace_park(scene->device, scene->d_wf, scene->wf_bytes);
-    scene->d_wf = nullptr;
-  }
-  /* stream-ordered: the memory goes back to the pool once work queued before this point on
-   * the legacy default stream (which synchronises with every blocking stream) is done */
-  void *bufs[] = { scene->d_nodes4q, scene->d_nodes4, scene->d_nodes, scene->d_prims, scene->d_big, scene->d_mats, scene->d_colors, scene->d_tex,
-                   scene->d_scratch, scene->d_counters };
-  for (void *b : bufs)
-    if (b)
-      cudaFreeAsync(b, 0);
+    rtb_cache_park(scene->device, scene->d_wf, scene->wf_bytes);
+  if (scene->d_scratch)
+    rtb_cache_park(scene->device, scene->d_scratch, scene->scratch_bytes);
   delete scene;
 }

@@ -562,7 +562,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     scene->d_wf = nullptr;
     scene->wf_bytes = 0;
     size_t got = 0;
-    if (void *parked = rtb_workspace_take(scene->device, need, &got))
+    if (void *parked = rtb_cache_take(scene->device, need, &got))
     {
       scene->d_wf = parked;
       scene->wf_bytes = got;

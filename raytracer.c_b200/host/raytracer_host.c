@@ -11,6 +11,8 @@
  * unchanged callers link against them (test.c uses calculate_surface_normal); they are
  * conveniences for host code, not a rendering fallback.
  */
+#include <time.h>
+
 #include "raytracer.h"
 #include "rtb200.h"
 
@@ -202,13 +204,27 @@ void render(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *cam
   render_ex(framebuffer, objects, n_objects, camera, options, NULL);
 }
 
+static double now_ms(void)
+{
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
+}
+
 void render_scene(uint8_t *framebuffer, SceneObject *objects, size_t n_objects, Camera *camera,
                   Options *options, const RenderParams *params)
 {
   rtb_scene *scene = NULL;
   int device = params ? params->device : 0;
+  const int timing = getenv("RTB_TIMING") != NULL; /* development aid: where an end-to-end call spends its time */
+  double t0 = now_ms();
   if (rtb_scene_create(objects, n_objects, device, &scene) != RTB_OK)
     die("render_scene: scene upload");
+  double t1 = now_ms();
   render_on_scene(framebuffer, scene, camera, options, params);
+  double t2 = now_ms();
   rtb_scene_destroy(scene);
+  double t3 = now_ms();
+  if (timing)
+    fprintf(stderr, "render_scene: create %.1f ms, render %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2);
 }
