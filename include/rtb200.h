@@ -117,8 +117,9 @@ int rtb_scene_create(const void *scene_objects96, size_t n_objects, int device, 
 int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info);
 void rtb_scene_destroy(rtb_scene *scene);
 
-/* The wavefront kernels' workspace (ray queues, up to 11.7 GB) is parked per device when a scene is
- * destroyed and reused by the next scene; this returns the parked buffer of `device` to the driver. */
+/* A destroyed scene parks its device buffers (scene arrays and the wavefront kernels' ray queues, up
+ * to 11.7 GB) in a per-device cache and the next scene reuses them, so that render() -- one scene per
+ * call -- allocates nothing in steady state.  This returns everything cached for `device` to the driver. */
 void rtb_release_workspace(int device);
 
 /* d_accum: DEVICE float[height*width*3], OVERWRITTEN with the sum over the call's samples.

@@ -989,7 +989,9 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
         k_emit4_seed<<<1, 1>>>(eq);
         /* a BVH4 level consumes at least one BVH2 level; an empty level costs an empty launch */
         const int half_blocks = (int)((N / 2 + T) / T);
-        for (int level = 0; level < RTB_STACK_SIZE; level++)
+        /* (a tree over N primitives has fewer than N levels: small scenes skip the empty launches) */
+        const int max_levels = (int)std::min<size_t>(RTB_STACK_SIZE, N);
+        for (int level = 0; level < max_levels; level++)
           k_emit4<<<half_blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
                                       d_node_hi.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, eq, level, leaf_max);
         RTB_CUDA(cudaGetLastError());
