@@ -661,9 +661,22 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   long long want_threads = 148ll * 2048 * 2;
   if (wavefront)
   {
-    size_t free_b = 0, total_b = 0;
-    RTB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    want_threads = std::min<long long>(64ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 192));
+    /* the free memory is read once per device (cudaMemGetInfo costs milliseconds, render() makes a
+     * new scene per call); it also keeps the plane count -- and with it the summation order --
+     * the same from call to call */
+    static long long path_cap[64] = { 0 };
+    const int dev = scene->device;
+    if (dev < 0 || dev >= 64 || path_cap[dev] == 0)
+    {
+      size_t free_b = 0, total_b = 0;
+      RTB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const long long cap = std::max<long long>(1ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 192));
+      if (dev >= 0 && dev < 64)
+        path_cap[dev] = cap;
+      want_threads = std::min<long long>(64ll << 20, cap);
+    }
+    else
+      want_threads = std::min<long long>(64ll << 20, path_cap[dev]);
     want_threads = std::max<long long>(want_threads, (long long)n_px);
   }
   int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);

@@ -1151,25 +1151,35 @@ void rtb_cache_park(int device, void *p, size_t bytes)
 {
   if (!p)
     return;
-  void *drop = p;
+  std::vector<void *> drop;
   if (device >= 0 && device < 64)
   {
+    /* keep at most kCacheEntries buffers and an eighth of the device memory; oldest go first */
+    static size_t total_mem[64] = { 0 }; /* cudaMemGetInfo costs milliseconds: asked once per device */
     std::lock_guard<std::mutex> lock(g_cache_mutex);
+    if (total_mem[device] == 0)
+    {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      total_mem[device] = total_b ? total_b : 1;
+    }
+    const size_t cap = std::max<size_t>(total_mem[device] / 8, bytes);
     std::vector<ParkedBuffer> &c = g_cache[device];
     c.push_back(ParkedBuffer{ p, bytes });
-    drop = nullptr;
-    if (c.size() > kCacheEntries)
+    size_t held = 0;
+    for (const ParkedBuffer &b : c)
+      held += b.bytes;
+    while (c.size() > 1 && (c.size() > kCacheEntries || held > cap))
     {
-      size_t smallest = 0;
-      for (size_t k = 1; k < c.size(); k++)
-        if (c[k].bytes < c[smallest].bytes)
-          smallest = k;
-      drop = c[smallest].p;
-      c.erase(c.begin() + (long)smallest);
+      held -= c.front().bytes;
+      drop.push_back(c.front().p);
+      c.erase(c.begin());
     }
   }
-  if (drop)
-    cudaFree(drop);
+  else
+    drop.push_back(p);
+  for (void *d : drop)
+    cudaFree(d);
 }
 
 extern "C" void rtb_release_workspace(int device)
