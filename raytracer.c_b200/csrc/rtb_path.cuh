@@ -139,7 +139,10 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
     {
       p = d3_make(__dadd_rn(__dmul_rn(px, 2.0), -1.0), __dadd_rn(__dmul_rn(py, 2.0), -1.0),
                   __dadd_rn(__dmul_rn(pz, 2.0), -1.0));
-      if (!(d3_length(p) > 1.0) || k >= 98u)
+      /* vec3_length(p) > 1.0 (raytracer.c:236) without the square root, exactly: for the
+       * correctly rounded sqrt, sqrt(x) > 1 <=> x > 1 + 2^-52 (sqrt(1 + 2^-52) = 1 + 2^-53 - ...
+       * rounds to 1; sqrt(1 + 2^-51) = 1 + 2^-52 - ... rounds to 1 + 2^-52) */
+      if (!(d3_dot(p, p) > 1.0000000000000002) || k >= 98u)
         break;
       k++;
       r = philox4x32_10(make_uint4(pixel, sample, bounce_word, k), A.key);
