@@ -341,6 +341,13 @@ def tonemap(d_accum_ptr, width, height, total_samples, d_fb_ptr, device=0, strea
                           C.c_void_p(stream or 0)), "rtb_tonemap")
 
 
+def release_workspace(device=0):
+    """give the per-device cache of parked buffers (ray queues, scene arrays) back to the driver"""
+    cu, _ = load()
+    cu.rtb_release_workspace.restype = None
+    cu.rtb_release_workspace(C.c_int(device))
+
+
 def probe_l2_bandwidth(nbytes=32 << 20, iters=50, device=0):
     """read bandwidth (GB/s) of an L2-resident buffer: the denominator for the walk's algorithmic bytes"""
     cu, _ = load()

@@ -716,6 +716,17 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     {
       int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr && desc->profile != 0, launches,
                           (counters && desc->profile != 0) ? phase_ms : nullptr);
+      /* the free memory was sampled once per device: if the queues no longer fit, halve the wave
+       * (only when the caller did not pin the plane count, which fixes the summation order) */
+      while (wrc == RTB_ENOMEM && desc->planes == 0 && A.splits > 1)
+      {
+        A.splits = (A.splits + 1) / 2;
+        A.chunk = (spp + A.splits - 1) / A.splits;
+        A.splits = (spp + A.chunk - 1) / A.chunk;
+        launches = 0;
+        wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr && desc->profile != 0, launches,
+                        (counters && desc->profile != 0) ? phase_ms : nullptr);
+      }
       if (wrc != RTB_OK)
         return wrc;
     }

@@ -569,7 +569,13 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     }
     else
     {
-      RTB_CUDA(cudaMalloc(&scene->d_wf, need));
+      if (cudaMalloc(&scene->d_wf, need) != cudaSuccess)
+      {
+        cudaGetLastError(); /* not sticky: the caller retries with fewer planes */
+        scene->d_wf = nullptr;
+        rtb_set_error("wavefront: not enough device memory for the ray queues");
+        return RTB_ENOMEM;
+      }
       scene->wf_bytes = need;
     }
   }

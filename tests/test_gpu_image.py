@@ -148,6 +148,30 @@ def test_workspace_is_reused_across_scenes(gpu_api):
     assert max(used[1:]) - min(used[1:]) < (64 << 20), used
 
 
+def test_wave_shrinks_when_memory_is_short(gpu_api):
+    """the ray queues want up to 11.7 GB; with little free memory the render must still succeed
+    (smaller waves), and give the same image up to float summation order"""
+    import torch
+    W, H, SPP = 1920, 1080, 32
+    objs = gpu_api.scene_default(W, H)
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        _, ref, c0 = sc.render(cam, gpu_api.make_desc(W, H, 0, SPP), want_accum=True)
+    gpu_api.release_workspace(0)
+    torch.cuda.synchronize()
+    free, total = torch.cuda.mem_get_info()
+    hog = torch.empty(max(0, free - (5 << 30)), dtype=torch.uint8, device="cuda")  # leave ~5 GB
+    try:
+        with gpu_api.Scene(objs) as sc:
+            _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 0, SPP), want_accum=True)
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+        gpu_api.release_workspace(0)
+    assert c1.rays == c0.rays and c1.paths == c0.paths
+    np.testing.assert_allclose(acc, ref, rtol=1e-5, atol=1e-5)
+
+
 def test_wavefront_depth_zero_and_empty(gpu_api):
     """max_depth 0 (one vertex per path) and an empty sample range"""
     W, H = 64, 36
