@@ -50,10 +50,6 @@ struct WfQueue
   uint4 *hit;     /* best.t (two words), gid, slot */
 };
 
-struct WfCounters
-{
-  unsigned long long *totals; /* scene->d_counters: rays, rays_hit, prim_tests, node_visits, paths */
-};
 
 __device__ __forceinline__ uint4 pack_hit(const HitRec &h)
 {
@@ -413,7 +409,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
 }
 
 template <int V>
-static void launch_trace(bool stats, int blocks_per_sm_unused, int sm_count, cudaStream_t stream, const SceneView &sv,
+static void launch_trace(bool stats, int sm_count, cudaStream_t stream, const SceneView &sv,
                          const WfQueue &q, const unsigned *n_ptr, unsigned *fetch, unsigned long long *totals,
                          int refill_idle, int node_exit, const unsigned *perm)
 {
@@ -641,14 +637,14 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       mark();
       switch (variant)
       {
-      case 2: launch_trace<2>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 4: launch_trace<4>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 18: launch_trace<18>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 22: launch_trace<22>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 10: launch_trace<10>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 14: launch_trace<14>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 6: launch_trace<6>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      default: launch_trace<0>(stats, 0, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 2: launch_trace<2>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 4: launch_trace<4>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 18: launch_trace<18>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 22: launch_trace<22>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 10: launch_trace<10>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 14: launch_trace<14>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      case 6: launch_trace<6>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
+      default: launch_trace<0>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       }
       mark();
       if (sort_out) /* slots beyond the queue's end keep the largest key and sort to the back */
