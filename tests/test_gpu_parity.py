@@ -332,3 +332,43 @@ def test_deep_unbalanced_tree(gpu_api, abi):
     print("bvh depth", info.bvh_depth, "hit fraction", (brute["ids"] >= 0).mean())
     assert (brute["ids"] >= 0).mean() > 0.5 and info.bvh_depth >= 12
     assert np.array_equal(a4, a6) and c4.rays == c6.rays
+
+
+def test_tree_walks_on_adversarial_rays(gpu_api):
+    """rays aimed exactly at mesh vertices and edge midpoints (ties between neighbouring
+    triangles, hits on box faces), axis-aligned rays (zero direction components) and rays that
+    start far outside the scene: BVH2, while-while, BVH4 and compressed BVH4 walks all return
+    the brute-force loop's nearest hit, bit for bit"""
+    W, H = 96, 54
+    verts = gpu_api.heightfield_mesh(100, 20 * W / H * 0.98)  # 20 000 triangles
+    holder = gpu_api.mesh_room(verts, W, H)
+    pos = verts["pos"].reshape(-1, 3, 3)
+    rng = np.random.default_rng(2024)
+    pick = rng.integers(0, len(pos), 6000)
+    targets = np.concatenate([
+        pos[pick[:2000], rng.integers(0, 3, 2000)],                       # vertices
+        0.5 * (pos[pick[2000:4000], 0] + pos[pick[2000:4000], 1]),         # edge midpoints
+        pos[pick[4000:]].mean(axis=1),                                     # centroids
+    ])
+    origins = np.concatenate([
+        rng.uniform(-25, 25, (3000, 3)) * np.array([1.0, 0.3, 1.0]) + np.array([0.0, 8.0, 0.0]),  # inside the room
+        rng.normal(size=(3000, 3)) * 400.0 + np.array([0.0, 600.0, 0.0]),                           # far outside
+    ])
+    d = targets - origins
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = [np.concatenate([origins, d], axis=1)]
+    # axis-aligned rays straight down / sideways through vertices: direction components exactly 0
+    t2 = pos[rng.integers(0, len(pos), 1500), 0]
+    for axis, sign in ((1, -1.0), (0, 1.0), (2, -1.0)):
+        dd = np.zeros((500, 3))
+        dd[:, axis] = sign
+        oo = t2[500 * (axis % 3):500 * (axis % 3) + 500] - dd * 30.0
+        rays.append(np.concatenate([oo, dd], axis=1))
+    rays = np.concatenate(rays)
+    with gpu_api.Scene(holder) as sc:
+        brute = sc.trace_rays(rays, use_bvh=0)
+        for mode in (1, 3, 4, 5):
+            got = sc.trace_rays(rays, use_bvh=mode)
+            for k in ("ids", "prims", "t", "points", "normals"):
+                assert np.array_equal(got[k], brute[k]), (mode, k)
+    assert (brute["ids"] >= 0).mean() > 0.9
