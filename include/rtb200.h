@@ -111,9 +111,14 @@ const char *rtb_last_error(void);
 const char *rtb_version(void);
 int rtb_device_count(void);
 
-/* scene: upload + marshal + BVH build (blocking) */
+/* scene: upload + marshal + BVH build (blocking).  The product path builds and walks ONE tree, the
+ * compressed BVH4.  RTB_SCENE_ALL_TREES also keeps the BVH2 and the uncompressed BVH4 the parity
+ * probes and the megakernel variants walk (rtb_trace_rays use_bvh 1..4, rtb_render_desc.kernel 1..5). */
+#define RTB_SCENE_ALL_TREES 1u
 int rtb_scene_create_objects(const void *objects88, size_t n_objects, int device, rtb_scene **out);
 int rtb_scene_create(const void *scene_objects96, size_t n_objects, int device, rtb_scene **out);
+int rtb_scene_create_objects_flags(const void *objects88, size_t n_objects, int device, unsigned flags, rtb_scene **out);
+int rtb_scene_create_flags(const void *scene_objects96, size_t n_objects, int device, unsigned flags, rtb_scene **out);
 int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info);
 void rtb_scene_destroy(rtb_scene *scene);
 

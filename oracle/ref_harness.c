@@ -284,3 +284,69 @@ double ref_random_double_from(int32_t r31)
   g_stream = NULL;
   return d;
 }
+
+/* ---- the tinyobj path (north_star: "the tinyobj OBJ loading path") -----------------------------
+ * The reference vendors tinyobjloader-c and compiles it into raytracer.c (raytracer.c:4-5) but never
+ * defines load_obj (raytracer.h:158).  This is the loader a maintainer would write on top of it,
+ * following SURVEY.md 8(f) N1: tinyobj_parse_obj(..., TINYOBJ_FLAG_TRIANGULATE), pos from the float
+ * `v` records, tex from `vt` or (0,0) when absent.  The product's load_obj (host/obj_loader.c, which
+ * does NOT use tinyobj) is compared against it by tests/test_obj_loader.py.
+ * out: 5 doubles per corner (pos.xyz, tex.uv), 3 corners per triangle; returns the triangle count,
+ * or -1 on failure; with out == NULL only counts. */
+static void ref_file_reader(void *ctx, const char *filename, int is_mtl, const char *obj_filename, char **buf, size_t *len)
+{
+  (void)ctx; (void)obj_filename;
+  *buf = NULL;
+  *len = 0;
+  if (is_mtl)
+    return; /* materials are per object in raytracer.h, the .mtl is not needed */
+  FILE *f = fopen(filename, "rb");
+  if (!f)
+    return;
+  fseek(f, 0, SEEK_END);
+  long size = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  char *data = (char *)malloc((size_t)size + 1);
+  if (data && fread(data, 1, (size_t)size, f) == (size_t)size)
+  {
+    data[size] = '\0';
+    *buf = data; /* tinyobj does not take ownership; freed by the next call or leaked (test code) */
+    *len = (size_t)size;
+  }
+  fclose(f);
+}
+
+long long ref_tinyobj_load(const char *path, double *out, long long capacity_triangles)
+{
+  tinyobj_attrib_t attrib;
+  tinyobj_shape_t *shapes = NULL;
+  tinyobj_material_t *materials = NULL;
+  size_t n_shapes = 0, n_materials = 0;
+  tinyobj_attrib_init(&attrib);
+  int rc = tinyobj_parse_obj(&attrib, &shapes, &n_shapes, &materials, &n_materials, path, ref_file_reader, NULL,
+                             TINYOBJ_FLAG_TRIANGULATE);
+  if (rc != TINYOBJ_SUCCESS)
+    return -1;
+  long long n_tris = (long long)attrib.num_faces / 3;
+  if (out)
+  {
+    if (n_tris > capacity_triangles)
+      n_tris = capacity_triangles;
+    for (long long c = 0; c < 3 * n_tris; c++)
+    {
+      tinyobj_vertex_index_t ix = attrib.faces[c];
+      double *o = out + 5 * c;
+      o[0] = attrib.vertices[3 * ix.v_idx + 0];
+      o[1] = attrib.vertices[3 * ix.v_idx + 1];
+      o[2] = attrib.vertices[3 * ix.v_idx + 2];
+      const int has_vt = ix.vt_idx >= 0 && (unsigned)ix.vt_idx != TINYOBJ_INVALID_INDEX &&
+                         (unsigned)ix.vt_idx < attrib.num_texcoords;
+      o[3] = has_vt ? attrib.texcoords[2 * ix.vt_idx + 0] : 0.0;
+      o[4] = has_vt ? attrib.texcoords[2 * ix.vt_idx + 1] : 0.0;
+    }
+  }
+  tinyobj_attrib_free(&attrib);
+  tinyobj_shapes_free(shapes, n_shapes);
+  tinyobj_materials_free(materials, n_materials);
+  return n_tris;
+}

@@ -20,6 +20,7 @@ LIB_HOST = os.path.join(_HERE, "libraytracer_b200.so")
 # every symbol include/rtb200.h declares
 RTB_SYMBOLS = [
     "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_scene_create_objects", "rtb_scene_create",
+    "rtb_scene_create_objects_flags", "rtb_scene_create_flags",
     "rtb_scene_info_get", "rtb_scene_destroy", "rtb_release_workspace", "rtb_render_accum", "rtb_tonemap", "rtb_render",
     "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth", "rtb_cast_rays",
 ]
@@ -64,6 +65,8 @@ def _bind(cu, host):
     cu.rtb_device_count.restype = C.c_int
     cu.rtb_scene_create_objects.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
     cu.rtb_scene_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    cu.rtb_scene_create_objects_flags.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
+    cu.rtb_scene_create_flags.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
     cu.rtb_scene_info_get.argtypes = [C.c_void_p, C.POINTER(abi.RtbSceneInfo)]
     cu.rtb_scene_destroy.argtypes = [C.c_void_p]
     cu.rtb_scene_destroy.restype = None
@@ -242,19 +245,22 @@ class Scene:
     """Device-resident scene (SoA geometry + BVH).  `source` is a structured Object array
     (spheres) or an abi.SceneHolder (spheres and meshes)."""
 
-    def __init__(self, source, device=0):
+    def __init__(self, source, device=0, all_trees=False):
+        """all_trees: also build the BVH2 and the uncompressed BVH4 (RTB_SCENE_ALL_TREES) that the
+        parity probes (trace_rays use_bvh 2..4) and the megakernel variants (kernel 1..5) walk"""
         cu, _ = load()
         self._cu = cu
         self._h = C.c_void_p()
         self.device = device
+        flags = 1 if all_trees else 0
         if isinstance(source, abi.SceneHolder):
             self._src = source
-            _check(cu.rtb_scene_create(C.addressof(source.objects), source.n, device, C.byref(self._h)),
+            _check(cu.rtb_scene_create_flags(C.addressof(source.objects), source.n, device, flags, C.byref(self._h)),
                    "rtb_scene_create")
         else:
             arr = np.ascontiguousarray(source, dtype=abi.OBJECT_DTYPE)
             self._src = arr
-            _check(cu.rtb_scene_create_objects(arr.ctypes.data, len(arr), device, C.byref(self._h)),
+            _check(cu.rtb_scene_create_objects_flags(arr.ctypes.data, len(arr), device, flags, C.byref(self._h)),
                    "rtb_scene_create_objects")
 
     def close(self):

@@ -362,6 +362,29 @@ struct WalkStack
     }
     return RTB_REF_NONE;
   }
+  /* same result, but the top TWO entries are read together: one round trip to local memory per
+   * two culled entries (the dependent load of the pop loop was 12.5 % of the walk's stall samples
+   * at 3 active lanes, profiles/r1_wf_trace_ncu.md) */
+  __device__ __forceinline__ int pop2(const RayF &rf)
+  {
+    while (sp > 0)
+    {
+      const int2 e0 = get(sp - 1);
+      const int2 e1 = get(sp > 1 ? sp - 2 : sp - 1);
+      if (__int_as_float(e0.y) <= rf.tmax)
+      {
+        sp -= 1;
+        return e0.x;
+      }
+      if (sp > 1 && __int_as_float(e1.y) <= rf.tmax)
+      {
+        sp -= 2;
+        return e1.x;
+      }
+      sp = sp > 1 ? sp - 2 : 0;
+    }
+    return RTB_REF_NONE;
+  }
 };
 
 /* 256-bit read-only global load (pointer must be 32-byte aligned) */
@@ -460,39 +483,59 @@ __device__ __forceinline__ int node_step4(const SceneView &sv, const RayF &rf, i
   return ref[0];
 }
 
-/* One compressed BVH4 node (Bvh4QNode): slab distances straight from the quantised planes,
- * t = q * (2^e / d) + (origin - o) / d */
-/* byte k of w as a float: I2F.U8 with a byte selector, one instruction (a PRMT + FADD
- * formulation that avoids the conversion pipe measured 4 % slower) */
+/* One compressed BVH4 node (Bvh4QNode, rtb_internal.h): slab distances straight from the
+ * quantised planes, t = q * (2^e / d) + (origin - o) / d.
+ *
+ * Instruction budget (profiles/r2_wf_trace_ncu.md): the round-1 form of this function was 148
+ * SASS instructions per visit, 100 of them on the ALU pipe (2 cycles per warp instruction) and 24
+ * I2F.U8 on the conversion pipe -- both pipes as busy as the issue slots.  This form
+ *   - picks the near/far plane word per AXIS from the sign of the ray direction (6 SEL per node)
+ *     instead of min/max-ing both planes per child (44 -> 16 FMNMX/FMNMX3);
+ *   - needs no validity test per child: an empty slot is an inverted box (qlo 255, qhi 0) whose
+ *     reference is a degenerate triangle at the end of the primitive array, so even a rounding
+ *     coincidence cannot send the walk to a bad address;
+ *   - reads the per-axis cell size as a ready float (no exponent-byte extraction);
+ *   - converts CONV_ALU of the 24 plane bytes on the ALU + FMA pipes (PRMT into the mantissa of
+ *     2^23, FADD -2^23) instead of the conversion pipe, to balance the three pipes. */
 __device__ __forceinline__ float qbyte(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
+/* byte k of w as a float without the conversion pipe: 0x4B0000bb = 2^23 + bb exactly */
+__device__ __forceinline__ float qbyte_alu(unsigned w, int k)
+{
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (unsigned)k)) - 8388608.0f;
+}
 
-template <class STK>
+template <int CONV_ALU, class STK>
 __device__ __forceinline__ int node_step4q(const SceneView &sv, const RayF &rf, int cur, STK &stack)
 {
   const float4 *np = sv.nodes4q + 4 * (size_t)cur;
   float4 w0, w1, w2, w3;
   ld256_nc(np + 0, w0, w1);
   ld256_nc(np + 2, w2, w3);
-  const unsigned eb = __float_as_uint(w0.w);
-  const float sx = __uint_as_float((eb & 0xFFu) << 23) * rf.idx;
-  const float sy = __uint_as_float(((eb >> 8) & 0xFFu) << 23) * rf.idy;
-  const float sz = __uint_as_float(((eb >> 16) & 0xFFu) << 23) * rf.idz;
+  const float sx = w0.w * rf.idx, sy = w3.z * rf.idy, sz = w3.w * rf.idz;
   const float bx = fmaf(w0.x, rf.idx, -rf.oodx), by = fmaf(w0.y, rf.idy, -rf.oody), bz = fmaf(w0.z, rf.idz, -rf.oodz);
   const unsigned qlx = __float_as_uint(w2.x), qly = __float_as_uint(w2.y), qlz = __float_as_uint(w2.z);
   const unsigned qhx = __float_as_uint(w2.w), qhy = __float_as_uint(w3.x), qhz = __float_as_uint(w3.y);
+  /* entry plane = lo for a positive direction component, hi for a negative one */
+  const bool nx = rf.idx < 0.0f, ny = rf.idy < 0.0f, nz = rf.idz < 0.0f;
+  const unsigned nrx = nx ? qhx : qlx, frx = nx ? qlx : qhx;
+  const unsigned nry = ny ? qhy : qly, fry = ny ? qly : qhy;
+  const unsigned nrz = nz ? qhz : qlz, frz = nz ? qlz : qhz;
   const float INF = 3.0e38f;
   float dist[4];
   int ref[4] = { __float_as_int(w1.x), __float_as_int(w1.y), __float_as_int(w1.z), __float_as_int(w1.w) };
 #pragma unroll
   for (int k = 0; k < 4; k++)
   {
-    const float ax = fmaf(qbyte(qlx, k), sx, bx), cx = fmaf(qbyte(qhx, k), sx, bx);
-    const float ay = fmaf(qbyte(qly, k), sy, by), cy = fmaf(qbyte(qhy, k), sy, by);
-    const float az = fmaf(qbyte(qlz, k), sz, bz), cz = fmaf(qbyte(qhz, k), sz, bz);
-    const float tmin = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), 0.0f));
-    const float tmax = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), rf.tmax));
-    const bool hit = (tmin <= tmax * RTB_WIDEN) && ref[k] != RTB_REF_NONE;
-    dist[k] = hit ? tmin : INF;
+    /* the first CONV_ALU far-plane conversions of the node go through PRMT + FADD */
+    const float ax = fmaf(qbyte(nrx, k), sx, bx);
+    const float ay = fmaf(qbyte(nry, k), sy, by);
+    const float az = fmaf(qbyte(nrz, k), sz, bz);
+    const float cx = fmaf((3 * k + 0 < CONV_ALU) ? qbyte_alu(frx, k) : qbyte(frx, k), sx, bx);
+    const float cy = fmaf((3 * k + 1 < CONV_ALU) ? qbyte_alu(fry, k) : qbyte(fry, k), sy, by);
+    const float cz = fmaf((3 * k + 2 < CONV_ALU) ? qbyte_alu(frz, k) : qbyte(frz, k), sz, bz);
+    const float tmin = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
+    const float tmax = fminf(fminf(cx, cy), fminf(cz, rf.tmax));
+    dist[k] = (tmin <= tmax * RTB_WIDEN) ? tmin : INF;
   }
   cswap(dist[0], ref[0], dist[1], ref[1]);
   cswap(dist[2], ref[2], dist[3], ref[3]);
@@ -507,12 +550,13 @@ __device__ __forceinline__ int node_step4q(const SceneView &sv, const RayF &rf, 
   return ref[0];
 }
 
-/* WIDE: 0 = BvhNode (two children, 64 B), 1 = Bvh4Node (128 B), 2 = Bvh4QNode (compressed, 64 B) */
+/* WIDE: 0 = BvhNode (two children, 64 B), 1 = Bvh4Node (128 B), 2 = Bvh4QNode (compressed, 64 B);
+ * 3, 4 = Bvh4QNode with 6 / 12 of the 24 byte conversions on the ALU + FMA pipes */
 template <int WIDE, class STK>
 __device__ __forceinline__ int node_step_w(const SceneView &sv, const RayF &rf, int cur, STK &stack)
 {
-  if (WIDE == 2)
-    return node_step4q(sv, rf, cur, stack);
+  if (WIDE >= 2)
+    return node_step4q<(WIDE - 2) * 6>(sv, rf, cur, stack);
   if (WIDE == 1)
     return node_step4(sv, rf, cur, stack);
   return node_step(sv, rf, cur, stack);

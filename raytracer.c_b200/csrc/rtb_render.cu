@@ -495,7 +495,7 @@ __global__ void k_trace_rays(const __grid_constant__ SceneView sv, const double 
   d3 d = d3_make(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
   HitRec best;
   TraceStats st = { 0u, 0u };
-  if (use_bvh == 5 && sv.nodes4q != nullptr)
+  if ((use_bvh == 5 || sv.nodes == nullptr) && use_bvh != 0 && sv.nodes4q != nullptr)
     closest_hit_ww<false, 0, 2>(sv, o, d, best, st, nullptr, 0);
   else if (use_bvh == 4 && sv.nodes4 != nullptr)
     closest_hit_ww<false, 0, 1>(sv, o, d, best, st, nullptr, 0);
@@ -548,7 +548,10 @@ __global__ void k_path_records(const __grid_constant__ RenderArgs A, int sample,
   while (st.alive)
   {
     HitRec best;
-    closest_hit<false, false>(A.sv, st.o, st.d, best, ts);
+    if (A.sv.nodes4q != nullptr)
+      closest_hit_ww<false, 0, 2>(A.sv, st.o, st.d, best, ts, nullptr, 0);
+    else
+      closest_hit<false, false>(A.sv, st.o, st.d, best, ts);
     d3 origin = st.o;
     Surface s;
     bool hit = best.t < 1e300;
@@ -658,6 +661,12 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
    * persistent trace kernel is amortised (measured C3: 8 M 3.07, 33 M 3.48, 66 M 3.61 Grays/s);
    * never more than a quarter of the free device memory. */
   const bool wavefront = desc->kernel == 6 || desc->kernel == 0;
+  if (!wavefront && desc->integrator == RTB_INTEGRATOR_PATH && scene->view.nodes == nullptr && scene->view.root_ref >= 0 &&
+      scene->view.root_ref != RTB_REF_NONE)
+  {
+    rtb_set_error("rtb_render_desc.kernel 1..5 walk the BVH2: create the scene with RTB_SCENE_ALL_TREES");
+    return RTB_EINVAL;
+  }
   long long want_threads = 148ll * 2048 * 2;
   if (wavefront)
   {
@@ -670,7 +679,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     {
       size_t free_b = 0, total_b = 0;
       RTB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      const long long cap = std::max<long long>(1ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 192));
+      const long long cap = std::max<long long>(1ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 256));
       if (dev >= 0 && dev < 64)
         path_cap[dev] = cap;
       want_threads = std::min<long long>(64ll << 20, cap);
@@ -889,6 +898,12 @@ extern "C" int rtb_trace_rays(rtb_scene *scene, const double *rays6, size_t n_ra
   }
   if (n_rays == 0)
     return RTB_OK;
+  if (use_bvh >= 2 && use_bvh <= 4 && scene->view.nodes == nullptr && scene->view.root_ref >= 0 &&
+      scene->view.root_ref != RTB_REF_NONE)
+  {
+    rtb_set_error("rtb_trace_rays: use_bvh 2..4 walk the BVH2 / uncompressed BVH4: create the scene with RTB_SCENE_ALL_TREES");
+    return RTB_EINVAL;
+  }
   RTB_CUDA(cudaSetDevice(scene->device));
   Dev<double> d_rays, d_ts, d_points, d_normals, d_uvs;
   Dev<int> d_ids;

@@ -339,18 +339,17 @@ __global__ void k_depth(int n, const int *__restrict__ parent_inner, const int *
                         int *__restrict__ max_depth)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  int depth = 0;
-  for (int node = parent_leaf[i]; node >= 0; node = parent_inner[node])
-    depth++;
+  int depth = 0; /* lanes past the end stay in the warp: the shuffle below names every lane */
+  if (i < n)
+    for (int node = parent_leaf[i]; node >= 0; node = parent_inner[node])
+      depth++;
   for (int off = 16; off > 0; off >>= 1)
     depth = max(depth, __shfl_xor_sync(0xFFFFFFFFu, depth, off));
   if ((threadIdx.x & 31) == 0)
     atomicMax(max_depth, depth);
 }
 
-__device__ __forceinline__ int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
+__host__ __device__ __forceinline__ int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
 
 /* one traversal node per inner node whose subtree holds more than RTB_LEAF_MAX primitives */
 __global__ void k_emit(const unsigned *__restrict__ vals, const float4 *__restrict__ box_lo,
@@ -421,7 +420,7 @@ __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restr
                         const int *__restrict__ range_first, const float4 *__restrict__ node_lo,
                         const float4 *__restrict__ node_hi, const BuildParams *__restrict__ bp,
                         float4 *__restrict__ out_nodes, float4 *__restrict__ out_nodes_q, Emit4Queues q, int level,
-                        int leaf_max)
+                        int leaf_max, int dummy_ref)
 {
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= q.counts[level])
@@ -510,19 +509,22 @@ __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restr
     for (int a = 0; a < 3; a++) { lo[m][a] = 0.0f; hi[m][a] = 0.0f; }
     ref[m] = RTB_REF_NONE;
   }
-  float4 *o = out_nodes + 8 * (size_t)i;
-  o[0] = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
-  o[1] = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
-  o[2] = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
-  o[3] = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
-  o[4] = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
-  o[5] = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
-  o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
-  o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (out_nodes) /* the uncompressed BVH4 is a parity probe (RTB_SCENE_ALL_TREES) */
+  {
+    float4 *o = out_nodes + 8 * (size_t)i;
+    o[0] = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+    o[1] = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+    o[2] = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+    o[3] = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+    o[4] = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+    o[5] = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+    o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
 
   /* compressed copy: per-node grid origin + q * 2^e, lo rounded down, hi rounded up */
-  float org[3];
-  unsigned ebyte[3], qlo[3] = { 0u, 0u, 0u }, qhi[3] = { 0u, 0u, 0u };
+  float org[3], cellf[3];
+  unsigned qlo[3] = { 0u, 0u, 0u }, qhi[3] = { 0u, 0u, 0u };
   for (int a = 0; a < 3; a++)
   {
     float nlo = 3.0e38f, nhi = -3.0e38f;
@@ -542,10 +544,10 @@ __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restr
     e = max(-126, min(127, e));
     double cell = ldexp(1.0, e);
     while (cell * 255.0 < ext && e < 127) { e++; cell = ldexp(1.0, e); }
-    ebyte[a] = (unsigned)(e + 127);
+    cellf[a] = (float)cell; /* a power of two in the normal range: exact */
     for (int k = 0; k < 4; k++)
     {
-      unsigned ql = 0u, qh = 0u;
+      unsigned ql = 255u, qh = 0u; /* empty slot: inverted box, never entered before it is left */
       if (ref[k] != RTB_REF_NONE)
       {
         double l = floor(((double)lo[k][a] - (double)nlo) / cell);
@@ -557,11 +559,15 @@ __global__ void k_emit4(const unsigned *__restrict__ vals, const float4 *__restr
       qhi[a] |= qh << (8 * k);
     }
   }
+  /* an empty slot refers to the degenerate triangle stored behind the last primitive */
+  for (int k = 0; k < 4; k++)
+    if (ref[k] == RTB_REF_NONE)
+      ref[k] = dummy_ref;
   float4 *oq = out_nodes_q + 4 * (size_t)i;
-  oq[0] = make_float4(org[0], org[1], org[2], __uint_as_float(ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16)));
-  oq[1] = o[6];
+  oq[0] = make_float4(org[0], org[1], org[2], cellf[0]);
+  oq[1] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
   oq[2] = make_float4(__uint_as_float(qlo[0]), __uint_as_float(qlo[1]), __uint_as_float(qlo[2]), __uint_as_float(qhi[0]));
-  oq[3] = make_float4(__uint_as_float(qhi[1]), __uint_as_float(qhi[2]), 0.0f, 0.0f);
+  oq[3] = make_float4(__uint_as_float(qhi[1]), __uint_as_float(qhi[2]), cellf[1], cellf[2]);
 }
 
 __global__ void k_reorder(const unsigned *__restrict__ vals, int n, const PrimRec *__restrict__ in,
@@ -770,8 +776,9 @@ std::vector<char> choose_big(const HostScene &hs)
   return big;
 }
 
-int build_scene(HostScene &hs, int device, rtb_scene **out)
+int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
 {
+  const bool all_trees = (flags & RTB_SCENE_ALL_TREES) != 0;
   int ndev = 0;
   RTB_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev)
@@ -863,6 +870,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
   BuildParams h_bp;
   memset(&h_bp, 0, sizeof(h_bp));
   int h_misc[2] = { 0, 0 };
+  int h_nodes4 = 0;
   bool bvh4_ok = true;
 
   if (N > 0)
@@ -921,7 +929,9 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     RTB_CUDA(cudaGetLastError());
     RTB_CUDA(cudaMemcpyAsync(&h_bp, d_bp.p, sizeof(h_bp), cudaMemcpyDeviceToHost, 0));
 
-    RTB_CUDA(scene_alloc(sc.get(), &sc->d_prims, 3 * N));
+    /* one record more than primitives: the degenerate triangle empty BVH4 slots refer to */
+    RTB_CUDA(scene_alloc(sc.get(), &sc->d_prims, 3 * (N + 1)));
+    RTB_CUDA(cudaMemsetAsync(sc->d_prims + 3 * N, 0, sizeof(PrimRec), 0)); /* all-zero triangle: det = 0, never hit */
     if (want_tex)
       RTB_CUDA(scene_alloc(sc.get(), &sc->d_tex, 3 * N));
 
@@ -973,12 +983,17 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       k_depth<<<blocks, T>>>((int)N, d_parent_inner.p, d_parent_leaf.p, d_misc.p);
       RTB_CUDA(cudaGetLastError());
 
-      RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes, 4 * (N - 1)));
-      RTB_CUDA(cudaMemsetAsync(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1), 0));
-      k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
-                            d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1, leaf_max);
-      RTB_CUDA(cudaGetLastError());
-      RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes4, 8 * (N - 1)));
+      /* the product path walks the compressed BVH4 only; the BVH2 and the uncompressed BVH4 are
+       * parity probes (RTB_SCENE_ALL_TREES) -- or the fallback for a tree too deep for the BVH4 stack */
+      if (all_trees)
+      {
+        RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes, 4 * (N - 1)));
+        RTB_CUDA(cudaMemsetAsync(sc->d_nodes, 0, sizeof(BvhNode) * (N - 1), 0));
+        k_emit<<<blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
+                              d_node_hi.p, d_bp.p, sc->d_nodes, d_misc.p + 1, leaf_max);
+        RTB_CUDA(cudaGetLastError());
+        RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes4, 8 * (N - 1)));
+      }
       RTB_CUDA(scene_alloc(sc.get(), &sc->d_nodes4q, 4 * (N - 1)));
       {
         Emit4Queues eq;
@@ -993,7 +1008,8 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
         const int max_levels = (int)std::min<size_t>(RTB_STACK_SIZE, N);
         for (int level = 0; level < max_levels; level++)
           k_emit4<<<half_blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
-                                      d_node_hi.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, eq, level, leaf_max);
+                                      d_node_hi.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, eq, level, leaf_max,
+                                      leaf_ref((int)N, 1));
         RTB_CUDA(cudaGetLastError());
         RTB_CUDA(cudaMemcpyAsync(h_levels, d_level_counts.p, sizeof(int) * (RTB_STACK_SIZE + 1), cudaMemcpyDeviceToHost, 0));
       }
@@ -1001,8 +1017,9 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
                                want_tex ? d_tex_unsorted.p : nullptr, sc->d_tex);
       RTB_CUDA(cudaGetLastError());
       RTB_CUDA(cudaMemcpyAsync(h_misc, d_misc.p, sizeof(h_misc), cudaMemcpyDeviceToHost, 0));
+      RTB_CUDA(cudaMemcpyAsync(&h_nodes4, d_misc4.p, sizeof(int), cudaMemcpyDeviceToHost, 0));
       view.root_ref = 0;
-      dev_bytes += (sizeof(BvhNode) + sizeof(Bvh4Node) + sizeof(Bvh4QNode)) * (N - 1);
+      dev_bytes += ((all_trees ? sizeof(BvhNode) + sizeof(Bvh4Node) : 0) + sizeof(Bvh4QNode)) * (N - 1);
     }
     dev_bytes += sizeof(PrimRec) * N + (want_tex ? sizeof(float2) * 3 * N : 0);
   }
@@ -1031,7 +1048,7 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
       view.guard_hi[k] = h_bp.guard_hi[k];
     }
     bvh_depth = h_misc[0];
-    n_nodes = (size_t)h_misc[1];
+    n_nodes = (size_t)h_nodes4; /* nodes of the tree the default path walks */
     int depth4 = 0;
     while (depth4 < RTB_STACK_SIZE && h_levels[depth4] > 0)
       depth4++;
@@ -1044,6 +1061,8 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
     /* a very unbalanced tree can be too deep for the BVH4 walk's stack while the BVH2 walk still
      * fits: such a scene is rendered with the BVH2 walk (same results, see SceneView::nodes4q) */
     bvh4_ok = 3 * depth4 <= RTB_STACK_SIZE - 2;
+    if (!bvh4_ok && !all_trees)
+      return build_scene(hs, device, flags | RTB_SCENE_ALL_TREES, out); /* rare: build the BVH2 as well */
   }
 
   view.nodes = sc->d_nodes;
@@ -1072,6 +1091,17 @@ int build_scene(HostScene &hs, int device, rtb_scene **out)
 
 extern "C" int rtb_scene_create(const void *scene_objects96, size_t n_objects, int device, rtb_scene **out)
 {
+  return rtb_scene_create_flags(scene_objects96, n_objects, device, 0u, out);
+}
+
+extern "C" int rtb_scene_create_objects(const void *objects88, size_t n_objects, int device, rtb_scene **out)
+{
+  return rtb_scene_create_objects_flags(objects88, n_objects, device, 0u, out);
+}
+
+extern "C" int rtb_scene_create_flags(const void *scene_objects96, size_t n_objects, int device, unsigned flags,
+                                      rtb_scene **out)
+{
   if (!out || (n_objects && !scene_objects96))
   {
     rtb_set_error("rtb_scene_create: NULL argument");
@@ -1082,10 +1112,11 @@ extern "C" int rtb_scene_create(const void *scene_objects96, size_t n_objects, i
   int rc = gather_scene_objects(static_cast<const RefSceneObject *>(scene_objects96), n_objects, hs);
   if (rc != RTB_OK)
     return rc;
-  return build_scene(hs, device, out);
+  return build_scene(hs, device, flags, out);
 }
 
-extern "C" int rtb_scene_create_objects(const void *objects88, size_t n_objects, int device, rtb_scene **out)
+extern "C" int rtb_scene_create_objects_flags(const void *objects88, size_t n_objects, int device, unsigned flags,
+                                              rtb_scene **out)
 {
   if (!out || (n_objects && !objects88))
   {
@@ -1107,7 +1138,7 @@ extern "C" int rtb_scene_create_objects(const void *objects88, size_t n_objects,
     push_material(hs, objs[i].flags, objs[i].color, objs[i].emission);
     hs.spheres.push_back(SphereIn{ objs[i].center.x, objs[i].center.y, objs[i].center.z, objs[i].radius, (int)i, (int)i });
   }
-  return build_scene(hs, device, out);
+  return build_scene(hs, device, flags, out);
 }
 
 extern "C" int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info)

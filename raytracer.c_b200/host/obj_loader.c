@@ -6,8 +6,10 @@
  * That third-party file is not copied here.  This is a small purpose-built reader with
  * the observable behaviour the tinyobj path would have for this use
  * (tinyobj_parse_obj(..., TINYOBJ_FLAG_TRIANGULATE), tinyobj_loader.h:118-144):
- *   - `v` positions and `vt` texcoords are parsed as double and narrowed to float
- *     (tinyobj_loader.h:470-481), so every coordinate is float-representable;
+ *   - `v` positions and `vt` texcoords are parsed as double with tinyobj's own (not correctly
+ *     rounded) decimal arithmetic and narrowed to float (tinyobj_loader.h:338-481), so every
+ *     coordinate is float-representable and equal to what the tinyobj path gives
+ *     (tests/test_obj_loader.py compares the two parsers bit for bit);
  *   - faces with more than 3 corners are fan-triangulated (i0, i[k-1], i[k])
  *     (tinyobj_loader.h:1203-1224); corners may be `v`, `v/vt`, `v//vn`, `v/vt/vn`;
  *   - indices are 1-based, negative indices are relative to the current count;
@@ -54,17 +56,101 @@ static const char *skip_blank(const char *p, const char *end)
   return p;
 }
 
+/* One real number, with the arithmetic of the reference's vendored parser so that the floats are
+ * the ones the tinyobj path produces (tinyobj_loader.h:338-468, restated, not copied): the token runs
+ * to the next blank; grammar [sign] digits [. digits] [(e|E) [sign] digits], parsed greedily;
+ *   - integer digits:    m = m * 10 + digit                       (double)
+ *   - k-th decimal digit: m += digit * (0.1 * 0.1 * ... k times)   (double, the power by repeated product)
+ *   - exponent e:        value = m * 5^e * 2^e, both powers by repeated product, inverted for e < 0
+ * and the double is narrowed to float (tinyobj_loader.h:470-481).  A token that does not start with a
+ * sign or a digit, or has no digit after the sign (".5", "-.5"), or an empty exponent, gives 0 -- as
+ * upstream, where the failure is silent.  Not strtod(): that one is correctly rounded, this is not,
+ * and the two differ in the last bit of the double for a few percent of inputs. */
 static bool parse_real(const char **pp, const char *end, float *out)
 {
   const char *p = skip_blank(*pp, end);
   if (p >= end)
     return false;
-  char *stop = NULL;
-  double val = strtod(p, &stop); /* the buffer is NUL-terminated */
-  if (stop == p)
-    return false;
-  *out = (float)val;
+  const char *stop = p;
+  while (stop < end && *stop != ' ' && *stop != '\t' && *stop != '\r' && *stop != '\n')
+    stop++;
   *pp = stop;
+  *out = 0.0f;
+
+  const char *c = p;
+  bool negative = false, exp_negative = false, ok = true;
+  double m = 0.0;
+  int e10 = 0, n_digits = 0;
+  if (*c == '+' || *c == '-')
+  {
+    negative = *c == '-';
+    c++;
+  }
+  else if (!isdigit((unsigned char)*c))
+    return true; /* value 0 */
+  for (; c < stop && isdigit((unsigned char)*c); c++, n_digits++)
+    m = m * 10 + (double)(*c - '0');
+  if (n_digits == 0)
+    return true;
+  if (c < stop && *c == '.')
+  {
+    c++;
+    for (int k = 1; c < stop && isdigit((unsigned char)*c); c++, k++)
+    {
+      double scale = 1.0;
+      for (int j = 0; j < k; j++)
+        scale *= 0.1;
+      m += (double)(*c - '0') * scale;
+    }
+  }
+  if (c < stop && (*c == 'e' || *c == 'E'))
+  {
+    c++;
+    if (c < stop && (*c == '+' || *c == '-'))
+    {
+      exp_negative = *c == '-';
+      c++;
+    }
+    else if (!(c < stop && isdigit((unsigned char)*c)))
+      ok = false;
+    int n_exp = 0;
+    for (; ok && c < stop && isdigit((unsigned char)*c); c++, n_exp++)
+      e10 = e10 * 10 + (*c - '0');
+    if (n_exp == 0)
+      ok = false;
+  }
+  if (!ok)
+    return true; /* value 0 */
+  double p5 = 1.0, p2 = 1.0;
+  for (int k = 0; k < e10; k++)
+    p5 = p5 * 5.0;
+  for (int k = 0; k < e10; k++)
+    p2 = p2 * 2.0;
+  if (exp_negative)
+  {
+    p5 = 1.0 / p5;
+    p2 = 1.0 / p2;
+  }
+  *out = (float)((negative ? -1 : 1) * (m * p5 * p2));
+  return true;
+}
+
+/* strtol() skips white space, newlines included: an index is only parsed where a digit or a
+ * sign actually starts before `end` (the end of the line), so `f 1// 2// 3//` keeps its three
+ * corners and a line ending in `/` never reads into the next line */
+static bool parse_index(const char **pp, const char *end, long *out)
+{
+  const char *p = *pp;
+  if (p >= end)
+    return false;
+  const char *q = p;
+  if (*q == '-' || *q == '+')
+    q++;
+  if (q >= end || !isdigit((unsigned char)*q))
+    return false;
+  char *stop = NULL;
+  *out = strtol(p, &stop, 10); /* the digits end at a non-digit no later than `end`'s newline or NUL */
+  *pp = stop <= end ? stop : end;
   return true;
 }
 
@@ -74,25 +160,19 @@ static bool parse_corner(const char **pp, const char *end, long *vi, long *ti)
   const char *p = skip_blank(*pp, end);
   if (p >= end || *p == '\n' || *p == '#')
     return false;
-  char *stop = NULL;
-  *vi = strtol(p, &stop, 10);
-  if (stop == p)
+  if (!parse_index(&p, end, vi))
     return false;
-  p = stop;
   *ti = 0;
   if (p < end && *p == '/')
   {
     p++;
-    if (p < end && *p != '/' && !isspace((unsigned char)*p))
-    {
-      *ti = strtol(p, &stop, 10);
-      p = stop;
-    }
+    long t = 0, n = 0;
+    if (parse_index(&p, end, &t))
+      *ti = t;
     if (p < end && *p == '/')
     {
       p++;
-      (void)strtol(p, &stop, 10); /* normal index, unused */
-      p = stop;
+      (void)parse_index(&p, end, &n); /* normal index, unused */
     }
   }
   *pp = p;
@@ -106,10 +186,14 @@ static bool resolve(long idx, size_t count, size_t *out)
     *out = (size_t)idx - 1;
     return true;
   }
-  if (idx < 0 && (size_t)(-idx) <= count)
+  if (idx < 0)
   {
-    *out = count - (size_t)(-idx);
-    return true;
+    const unsigned long back = 0ul - (unsigned long)idx; /* defined for LONG_MIN too */
+    if (back <= count)
+    {
+      *out = count - (size_t)back;
+      return true;
+    }
   }
   return false;
 }

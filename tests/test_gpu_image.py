@@ -65,7 +65,7 @@ def test_golden_hits_on_device(gpu_api):
     g = np.load(os.path.join(GOLD, "c1_hits.npz"))
     objs = gpu_api.scene_default(320, 180)
     rays = random_rays_in_room(np.random.default_rng(105), 3000)
-    with gpu_api.Scene(objs) as sc:
+    with gpu_api.Scene(objs, all_trees=True) as sc:
         for mode in (1, 2, 3, 4, 5, 0):  # BVH, BVH + FP32 pre-test, while-while, BVH4, compressed BVH4, brute force
             got = sc.trace_rays(rays, use_bvh=mode)
             assert np.array_equal(got["ids"], g["ids"]), mode
@@ -83,7 +83,7 @@ def test_kernel_variants_agree(gpu_api, kernel):
     W, H, SPP = 96, 54, 8
     objs = gpu_api.scene_sphere_field(400, W, H, mix=(0.3, 0.3, 0.3))
     cam = gpu_api.init_camera(W, H)
-    with gpu_api.Scene(objs) as sc:
+    with gpu_api.Scene(objs, all_trees=True) as sc:
         _, base, c0 = sc.render(cam, gpu_api.make_desc(W, H, 0, SPP, max_depth=8, kernel=0), want_accum=True)
         _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 0, SPP, max_depth=8, kernel=kernel), want_accum=True)
     assert np.array_equal(acc, base)
@@ -98,7 +98,7 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
     verts = gpu_api.heightfield_mesh(40, 20 * W / H * 0.98)
     holder = gpu_api.mesh_room(verts, W, H)
     cam = gpu_api.init_camera(W, H)
-    with gpu_api.Scene(holder) as sc:
+    with gpu_api.Scene(holder, all_trees=True) as sc:
         _, base, c0 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=4, planes=planes), want_accum=True)
         _, acc, c1 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes), want_accum=True)
         _, acc2, c2 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=(2 << 16) | (16 << 8) | 1), want_accum=True)  # BVH2 walk, refill at 1 idle lane
@@ -107,6 +107,10 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
         wideq = (22 << 16) | (16 << 8)  # compressed BVH4 walk
         _, acc5, c5 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=wideq), want_accum=True)
         assert np.array_equal(acc5, base) and c5.rays == c0.rays
+        # round 2: byte conversions split between the conversion and ALU/FMA pipes (32, 64), two-entry pops (128)
+        for v in (54, 86, 150, 182, 214, 278):
+            _, accv, cv = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=(v << 16) | (16 << 8)), want_accum=True)
+            assert np.array_equal(accv, base) and cv.rays == c0.rays and cv.prim_tests == c5.prim_tests, v
         _, acc4, c4 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune2=3), want_accum=True)
     assert np.array_equal(acc, base) and np.array_equal(acc2, base)
     assert np.array_equal(acc3, base) and c3.rays == c0.rays and c3.node_visits < c0.node_visits
@@ -177,7 +181,7 @@ def test_wavefront_depth_zero_and_empty(gpu_api):
     W, H = 64, 36
     objs = gpu_api.scene_default(W, H)
     cam = gpu_api.init_camera(W, H)
-    with gpu_api.Scene(objs) as sc:
+    with gpu_api.Scene(objs, all_trees=True) as sc:
         _, a0, c0 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=0, kernel=4), want_accum=True)
         _, a1, c1 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=0, kernel=6), want_accum=True)
         _, e, ce = sc.render(cam, gpu_api.make_desc(W, H, 5, 5, kernel=6), want_accum=True)
@@ -192,7 +196,7 @@ def test_full_size_properties(gpu_api):
     verts = gpu_api.heightfield_mesh(708, 20 * W / H * 0.98)
     holder = gpu_api.mesh_room(verts, W, H)
     cam = gpu_api.init_camera(W, H)
-    with gpu_api.Scene(holder) as sc:
+    with gpu_api.Scene(holder, all_trees=True) as sc:
         info = sc.info
         assert info.n_triangles == 1002528 and info.n_bvh_prims + info.n_big_prims == 1002528 + 12
         _, a, ca = sc.render(cam, gpu_api.make_desc(W, H, 0, 2), want_accum=True)

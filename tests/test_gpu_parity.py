@@ -320,7 +320,7 @@ def test_deep_unbalanced_tree(gpu_api, abi):
     rays = np.concatenate([o, d], axis=1)
     W, H = 64, 36
     cam = gpu_api.init_camera(W, H)
-    with gpu_api.Scene(objs) as sc:
+    with gpu_api.Scene(objs, all_trees=True) as sc:
         info = sc.info
         brute = sc.trace_rays(rays, use_bvh=0)
         for mode in (1, 3, 4, 5):
@@ -365,7 +365,7 @@ def test_tree_walks_on_adversarial_rays(gpu_api):
         oo = t2[500 * (axis % 3):500 * (axis % 3) + 500] - dd * 30.0
         rays.append(np.concatenate([oo, dd], axis=1))
     rays = np.concatenate(rays)
-    with gpu_api.Scene(holder) as sc:
+    with gpu_api.Scene(holder, all_trees=True) as sc:
         brute = sc.trace_rays(rays, use_bvh=0)
         for mode in (1, 3, 4, 5):
             got = sc.trace_rays(rays, use_bvh=mode)
