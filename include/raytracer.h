@@ -204,6 +204,9 @@ typedef struct
   int device;          /* CUDA device ordinal */
   float *accum_out;    /* optional HOST float[H*W*3] sum of samples (not the mean) */
   int integrator;      /* RT_INTEGRATOR_*: upstream picks at compile time (`#if 1`, raytracer.c:207) */
+  int num_gpus;        /* GPUs 0..num_gpus-1 of the box render disjoint sample ranges and one ncclReduce sums the
+                          float buffers on GPU 0 (rtb200.h); default 1, or $RTB_NUM_GPUS so that the unchanged
+                          main.c -- which calls render() without parameters -- can use the whole box */
 } RenderParams;
 
 void render_params_default(RenderParams *p);
@@ -217,6 +220,9 @@ void render_ex(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *
                Options *options, const RenderParams *params);
 
 void free_mesh(TriangleMesh *mesh);
+
+/* mesh placement helper of the reference's driver (main.c:140-147) */
+void apply_matrix(TriangleMesh *mesh, mat4 matrix);
 
 #ifdef __cplusplus
 }

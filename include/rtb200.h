@@ -19,6 +19,9 @@
  *                          Whitted integrator (rtb_render_desc.integrator = RTB_INTEGRATOR_WHITTED)
  *   rtb_philox4x32_10      random_double()'s replacement (raytracer.c:227): KAT probe
  *   rtb_probe_l2_bandwidth no reference counterpart: measures the L2 roofline denominator
+ *   rtb_comm_*, rtb_render_multi   render() on all GPUs of the box: spp-sharded, ONE ncclReduce of the
+ *                          float sums, sharded scene upload + all-gather (no reference counterpart:
+ *                          upstream is `#pragma omp parallel for` over rows, raytracer.c:184)
  *
  * Array arguments named `objects` are arrays of the reference's own records:
  *   - flat sphere record `Object`, 88 bytes (raytracer.h:104-111):
@@ -140,6 +143,11 @@ int rtb_tonemap(const float *d_accum, int width, int height, int total_samples, 
 int rtb_render(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
                uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters);
 
+/* same, with an explicit divisor of the mean: a caller that shards the sample range over several calls
+ * (sample_begin/end = its share) passes the job's total sample count */
+int rtb_render_mean(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc, int total_samples,
+                    uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters);
+
 /* parity probes (host buffers) */
 int rtb_trace_rays(rtb_scene *scene, const double *rays6, size_t n_rays, int use_bvh, int32_t *ids,
                    int64_t *prims, double *ts, double *points, double *normals, double *uvs);
@@ -152,6 +160,46 @@ int rtb_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, size_t n, uint
  * rgb: HOST double[3*n]; ray_counts (optional): cast_ray invocations per ray (ray_count, raytracer.c:558) */
 int rtb_cast_rays(rtb_scene *scene, const double *rays6, size_t n_rays, int max_depth, double *rgb,
                   unsigned long long *ray_counts);
+
+/* ---- all the GPUs of one box ------------------------------------------------------------------------
+ * Replaces nothing upstream (the reference is single-node CPU + OpenMP, raytracer.c:184); it is how
+ * render() (raytracer.h:156, call site main.c:429) uses more than one GPU.  The per-pixel sum of
+ * raytracer.c:199-213 is sharded over SAMPLES: rank r of G renders its share of the global sample
+ * range, the per-GPU float sums meet in one ncclReduce(sum) on rank 0 (NVLink / NVSwitch), rank 0 runs
+ * the gamma + quantise kernel.  The scene upload is sharded too: each rank sends 1/G of the triangles
+ * over its PCIe link and the marshalled records are all-gathered over NVLink.
+ *
+ * A comm is a group of ranks, one per GPU:
+ *   rtb_comm_create_rank    this process is ONE rank (one process per GPU: torchrun, mpirun); id128 comes
+ *                           from rtb_comm_unique_id on rank 0 and travels through the launcher's channel
+ *   rtb_comm_create_local   this process drives ALL ranks (devices[k] = CUDA ordinal of rank k, NULL = 0..n-1)
+ * Calls that take a comm are collective: every rank makes them with the same arguments; a local comm
+ * makes the per-rank calls itself, one host thread per GPU.  `scenes` / `scenes_out` are arrays of
+ * rtb_comm_local_ranks(comm) handles (1 or n).  `record_bytes` = 88 (Object) or 96 (SceneObject).
+ * desc->sample_begin/end is the WHOLE job's sample range. */
+typedef struct rtb_comm rtb_comm;
+#define RTB_UNIQUE_ID_BYTES 128
+int rtb_comm_unique_id(void *id128);
+int rtb_comm_create_rank(const void *id128, int rank, int n_ranks, int device, rtb_comm **out);
+int rtb_comm_create_local(const int *devices_or_null, int n_devices, rtb_comm **out);
+int rtb_comm_size(const rtb_comm *comm);
+int rtb_comm_local_ranks(const rtb_comm *comm);
+void rtb_comm_destroy(rtb_comm *comm);
+/* which global sample indices rank `rank` of `n_ranks` renders of [sample_begin, sample_end): contiguous,
+ * disjoint, covering, sizes differ by at most one (pure host arithmetic, no GPU needed) */
+int rtb_comm_shard_samples(int sample_begin, int sample_end, int rank, int n_ranks, int *begin_out, int *end_out);
+
+/* sharded upload + NVLink all-gather + per-GPU BVH build (blocking) */
+int rtb_comm_scene_create(rtb_comm *comm, const void *objects, size_t n_objects, int record_bytes, unsigned flags,
+                          rtb_scene **scenes_out);
+/* device-resident frame: accumulate (sharded) -> ncclReduce -> tonemap on rank 0 into d_fb_root (DEVICE
+ * u8[H*W*3] on rank 0's GPU, may be NULL: an internal buffer is used).  Asynchronous on each GPU's legacy
+ * default stream unless `counters` is given; counters are whole-job (sums over ranks, times = slowest rank) */
+int rtb_comm_render(rtb_comm *comm, rtb_scene *const *scenes, const double *camera12, const rtb_render_desc *desc,
+                    uint8_t *d_fb_root, rtb_counters *counters);
+/* whole render() with HOST buffers on all GPUs: scene in, framebuffer (+ optional float sums) out on rank 0 */
+int rtb_render_multi(rtb_comm *comm, const void *objects, size_t n_objects, int record_bytes, const double *camera12,
+                     const rtb_render_desc *desc, uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters);
 
 /* measurement probe: read bandwidth of an L2-resident buffer of `bytes` (128-bit ld.global.cg from every SM,
  * `iters` passes), in GB/s -- the denominator bench.py uses for the walk's L1/L2-served algorithmic bytes */

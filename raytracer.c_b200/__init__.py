@@ -7,5 +7,5 @@ package is only the ctypes view of those libraries used by tests/ and bench.py.
 The directory name contains a dot, so import it through `__graft_entry__.load_package()`
 (which registers it as `raytracer_c_b200`).
 """
-from . import abi, api, sharding  # noqa: F401
+from . import abi, api  # noqa: F401
 from .api import RtbError, Scene, load  # noqa: F401

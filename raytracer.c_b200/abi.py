@@ -79,7 +79,7 @@ class Options(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("max_depth", C.c_int), ("seed", C.c_uint64), ("sample_offset", C.c_int),
                 ("total_samples", C.c_int), ("dielectric_mode", C.c_int), ("device", C.c_int),
-                ("accum_out", C.POINTER(C.c_float)), ("integrator", C.c_int)]
+                ("accum_out", C.POINTER(C.c_float)), ("integrator", C.c_int), ("num_gpus", C.c_int)]
 
 
 class SceneMix(C.Structure):

@@ -23,13 +23,15 @@ RTB_SYMBOLS = [
     "rtb_scene_create_objects_flags", "rtb_scene_create_flags",
     "rtb_scene_info_get", "rtb_scene_destroy", "rtb_release_workspace", "rtb_render_accum", "rtb_tonemap", "rtb_render",
     "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth", "rtb_cast_rays",
+    "rtb_render_mean", "rtb_comm_unique_id", "rtb_comm_create_rank", "rtb_comm_create_local", "rtb_comm_size",
+    "rtb_comm_local_ranks", "rtb_comm_destroy", "rtb_comm_shard_samples", "rtb_comm_scene_create", "rtb_comm_render", "rtb_render_multi",
 ]
 # the reference's exported surface (raytracer.h:135-164) plus the documented extensions
 HOST_SYMBOLS = [
     "random_double", "random_range", "point_at", "calculate_surface_normal", "intersect_sphere",
     "intersect_triangle", "print_v", "print_m", "clamp", "init_camera", "render", "load_obj",
     "ray_count", "intersection_test_count",
-    "render_params_default", "render_scene", "render_ex", "free_mesh",
+    "render_params_default", "render_scene", "render_ex", "free_mesh", "apply_matrix",
     "scene_default", "scene_room_walls", "scene_random_spheres", "scene_sphere_field",
     "scene_heightfield_mesh", "scene_write_obj", "scene_mesh_room", "scene_from_objects", "rt_write_png",
 ]
@@ -80,6 +82,20 @@ def _bind(cu, host):
     cu.rtb_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     cu.rtb_cast_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     cu.rtb_probe_l2_bandwidth.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    cu.rtb_render_mean.argtypes = [C.c_void_p, dp, C.POINTER(abi.RtbRenderDesc), C.c_int, C.c_void_p, C.c_void_p,
+                                   C.POINTER(abi.RtbCounters)]
+    cu.rtb_comm_unique_id.argtypes = [C.c_void_p]
+    cu.rtb_comm_create_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    cu.rtb_comm_create_local.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    cu.rtb_comm_size.argtypes = [C.c_void_p]
+    cu.rtb_comm_local_ranks.argtypes = [C.c_void_p]
+    cu.rtb_comm_destroy.argtypes = [C.c_void_p]
+    cu.rtb_comm_destroy.restype = None
+    cu.rtb_comm_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
+    cu.rtb_comm_render.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), dp, C.POINTER(abi.RtbRenderDesc), C.c_void_p,
+                                   C.POINTER(abi.RtbCounters)]
+    cu.rtb_render_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, dp, C.POINTER(abi.RtbRenderDesc),
+                                    C.c_void_p, C.c_void_p, C.POINTER(abi.RtbCounters)]
 
     host.init_camera.argtypes = [C.POINTER(abi.Camera), abi.Vec3, abi.Vec3, C.POINTER(abi.Options)]
     host.init_camera.restype = None
@@ -339,6 +355,122 @@ class Scene:
                                          out["normals"].ctypes.data, out["dists"].ctypes.data,
                                          out["radiance"].ctypes.data), "rtb_path_records")
         return out
+
+
+# ---- all the GPUs of one box (rtb_comm_*, include/rtb200.h) ---------------------------------------
+
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rank 0 of a one-process-per-GPU job: the 128-byte id the other ranks need (send it through the
+    launcher's own channel, e.g. torch.distributed.broadcast)"""
+    cu, _ = load()
+    buf = (C.c_ubyte * UNIQUE_ID_BYTES)()
+    _check(cu.rtb_comm_unique_id(buf), "rtb_comm_unique_id")
+    return bytes(buf)
+
+
+def shard_samples(sample_begin, sample_end, rank, n_ranks):
+    """the sample range rank `rank` renders (rtb_comm_shard_samples; host arithmetic only)"""
+    cu, _ = load()
+    a, b = C.c_int(), C.c_int()
+    _check(cu.rtb_comm_shard_samples(sample_begin, sample_end, rank, n_ranks, C.byref(a), C.byref(b)),
+           "rtb_comm_shard_samples")
+    return a.value, b.value
+
+
+def _source_records(source):
+    """-> (pointer, count, record bytes, keep-alive) for a structured Object array or an abi.SceneHolder"""
+    if isinstance(source, abi.SceneHolder):
+        return C.addressof(source.objects), source.n, 96, source
+    arr = np.ascontiguousarray(source, dtype=abi.OBJECT_DTYPE)
+    return arr.ctypes.data, len(arr), 88, arr
+
+
+class Comm:
+    """A group of GPUs, one rank each.  Comm.rank(...) = this process is one rank (torchrun);
+    Comm.local(n) = this process drives n GPUs (what render() does for RenderParams.num_gpus > 1)."""
+
+    def __init__(self, handle):
+        cu, _ = load()
+        self._cu, self._h = cu, handle
+        self.size = cu.rtb_comm_size(handle)
+        self.local_ranks = cu.rtb_comm_local_ranks(handle)
+
+    @classmethod
+    def rank(cls, unique_id, rank, n_ranks, device):
+        cu, _ = load()
+        h = C.c_void_p()
+        buf = (C.c_ubyte * UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _check(cu.rtb_comm_create_rank(buf, rank, n_ranks, device, C.byref(h)), "rtb_comm_create_rank")
+        return cls(h)
+
+    @classmethod
+    def local(cls, n_devices, devices=None):
+        cu, _ = load()
+        h = C.c_void_p()
+        arr = (C.c_int * n_devices)(*devices) if devices is not None else None
+        _check(cu.rtb_comm_create_local(arr, n_devices, C.byref(h)), "rtb_comm_create_local")
+        return cls(h)
+
+    def close(self):
+        if self._h:
+            self._cu.rtb_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def scene(self, source, all_trees=False):
+        """collective: sharded upload + all-gather + per-GPU BVH build -> MultiScene"""
+        ptr, n, kind, keep = _source_records(source)
+        handles = (C.c_void_p * self.local_ranks)()
+        _check(self._cu.rtb_comm_scene_create(self._h, ptr, n, kind, 1 if all_trees else 0, handles),
+               "rtb_comm_scene_create")
+        return MultiScene(self, handles, keep)
+
+    def render_host(self, source, camera, desc, want_accum=False, want_counters=True):
+        """collective: the whole render() with host buffers on all GPUs (rtb_render_multi).
+        The framebuffer (and sums) are valid on the process that holds rank 0."""
+        ptr, n, kind, keep = _source_records(source)
+        cam = camera.as_array()
+        fb = np.zeros((desc.height, desc.width, 3), dtype=np.uint8)
+        acc = np.zeros((desc.height, desc.width, 3), dtype=np.float32) if want_accum else None
+        ctr = abi.RtbCounters() if want_counters else None
+        _check(self._cu.rtb_render_multi(self._h, ptr, n, kind, cam.ctypes.data_as(C.POINTER(C.c_double)), C.byref(desc),
+                                         fb.ctypes.data, acc.ctypes.data if want_accum else None,
+                                         C.byref(ctr) if ctr is not None else None), "rtb_render_multi")
+        return fb, acc, ctr
+
+
+class MultiScene:
+    def __init__(self, comm, handles, keep):
+        self._comm, self._handles, self._keep = comm, handles, keep
+
+    def render(self, camera, desc, d_fb_root_ptr=None, want_counters=False):
+        """collective, device-resident: accumulate (sample-sharded) -> ncclReduce -> tonemap on rank 0"""
+        cam = camera.as_array()
+        ctr = abi.RtbCounters() if want_counters else None
+        _check(self._comm._cu.rtb_comm_render(self._comm._h, self._handles, cam.ctypes.data_as(C.POINTER(C.c_double)),
+                                              C.byref(desc), C.c_void_p(d_fb_root_ptr or 0),
+                                              C.byref(ctr) if ctr is not None else None), "rtb_comm_render")
+        return ctr
+
+    def close(self):
+        for k in range(len(self._handles)):
+            if self._handles[k]:
+                self._comm._cu.rtb_scene_destroy(self._handles[k])
+                self._handles[k] = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def tonemap(d_accum_ptr, width, height, total_samples, d_fb_ptr, device=0, stream=None):

@@ -119,6 +119,20 @@ struct rtb_scene
 void *rtb_cache_take(int device, size_t need, size_t *bytes); /* NULL if nothing parked fits */
 void rtb_cache_park(int device, void *p, size_t bytes);       /* the device must be done with p */
 
+/* ---- multi-GPU (rtb_multi.cu) -------------------------------------------------------------------
+ * One rank per GPU.  `nccl` is an ncclComm_t (kept opaque here so that only rtb_multi.cu needs nccl.h). */
+struct rtb_scene_shard
+{
+  int rank, n_ranks;
+  void *nccl;
+};
+/* in-place all-gather (chunk `rank` of each array is this rank's) of the marshalled triangle records,
+ * their boxes and (optionally) texture coordinates, on the legacy default stream of the current device */
+int rtb_shard_allgather(const rtb_scene_shard *shard, void *prims, size_t prim_chunk_bytes, void *box_lo, void *box_hi,
+                        size_t box_chunk_bytes, void *tex_or_null, size_t tex_chunk_bytes);
+int rtb_scene_create_sharded(const void *objects, size_t n_objects, int kind, int device, unsigned flags,
+                             const rtb_scene_shard *shard, rtb_scene **out);
+
 /* error plumbing */
 void rtb_set_error(const std::string &msg);
 #define RTB_CUDA(call)                                                                         \

@@ -15,6 +15,8 @@
  */
 #include "rtb_path.cuh"
 
+#include <atomic>
+
 #include <algorithm>
 #include <vector>
 #include <cstring>
@@ -673,19 +675,19 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     /* the free memory is read once per device (cudaMemGetInfo costs milliseconds, render() makes a
      * new scene per call); it also keeps the plane count -- and with it the summation order --
      * the same from call to call */
-    static long long path_cap[64] = { 0 };
+    static std::atomic<long long> path_cap[64]; /* zero-initialised; scenes on several devices render from several host threads */
     const int dev = scene->device;
-    if (dev < 0 || dev >= 64 || path_cap[dev] == 0)
+    if (dev < 0 || dev >= 64 || path_cap[dev].load() == 0)
     {
       size_t free_b = 0, total_b = 0;
       RTB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      const long long cap = std::max<long long>(1ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 256));
+      const long long cap = std::max<long long>(1ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 192));
       if (dev >= 0 && dev < 64)
-        path_cap[dev] = cap;
+        path_cap[dev].store(cap);
       want_threads = std::min<long long>(64ll << 20, cap);
     }
     else
-      want_threads = std::min<long long>(64ll << 20, path_cap[dev]);
+      want_threads = std::min<long long>(64ll << 20, path_cap[dev].load());
     want_threads = std::max<long long>(want_threads, (long long)n_px);
   }
   int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);
@@ -700,7 +702,16 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
 
   unsigned long long launches = 0;
   float phase_ms[3] = { 0.0f, 0.0f, 0.0f };
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  struct EventPair /* destroyed on every return path */
+  {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair()
+    {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } evp;
+  cudaEvent_t &ev0 = evp.a, &ev1 = evp.b;
   if (counters)
   {
     RTB_CUDA(cudaEventCreate(&ev0));
@@ -815,8 +826,6 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     counters->trace_ms = phase_ms[0];
     counters->shade_ms = phase_ms[1];
     counters->trace_launches = (unsigned long long)phase_ms[2];
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
   }
   return RTB_OK;
 }
@@ -839,9 +848,16 @@ extern "C" int rtb_tonemap(const float *d_accum, int width, int height, int tota
 extern "C" int rtb_render(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
                           uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters)
 {
-  if (!scene || !framebuffer)
+  const int spp = desc ? desc->sample_end - desc->sample_begin : 0;
+  return rtb_render_mean(scene, camera12, desc, spp > 0 ? spp : 1, framebuffer, accum_or_null, counters);
+}
+
+extern "C" int rtb_render_mean(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc, int total_samples,
+                               uint8_t *framebuffer, float *accum_or_null, rtb_counters *counters)
+{
+  if (!scene || !framebuffer || total_samples <= 0)
   {
-    rtb_set_error("rtb_render: NULL argument");
+    rtb_set_error("rtb_render: NULL argument or total_samples <= 0");
     return RTB_EINVAL;
   }
   int rc = check_desc(desc);
@@ -860,9 +876,8 @@ extern "C" int rtb_render(rtb_scene *scene, const double *camera12, const rtb_re
     return RTB_ECUDA;
   }
   rc = rtb_render_accum(scene, camera12, desc, d_accum, nullptr, counters);
-  int spp = desc->sample_end - desc->sample_begin;
   if (rc == RTB_OK)
-    rc = rtb_tonemap(d_accum, desc->width, desc->height, spp > 0 ? spp : 1, d_fb, scene->device, nullptr);
+    rc = rtb_tonemap(d_accum, desc->width, desc->height, total_samples, d_fb, scene->device, nullptr);
   if (rc == RTB_OK)
   {
     cudaError_t e = cudaMemcpy(framebuffer, d_fb, n, cudaMemcpyDeviceToHost);

@@ -21,6 +21,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cfloat>
 #include <cstdlib>
@@ -615,8 +616,8 @@ struct HostScene
  * an unlimited release threshold: after the first scene, create/destroy recycle pool memory. */
 static cudaError_t pool_setup(int device)
 {
-  static bool done[64] = { false };
-  if (device < 64 && done[device])
+  static std::atomic<bool> done[64]; /* zero-initialised */
+  if (device < 64 && done[device].load())
     return cudaSuccess;
   cudaMemPool_t pool;
   cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
@@ -625,7 +626,7 @@ static cudaError_t pool_setup(int device)
   unsigned long long threshold = ~0ull;
   e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
   if (e == cudaSuccess && device < 64)
-    done[device] = true;
+    done[device].store(true);
   return e;
 }
 
@@ -776,7 +777,7 @@ std::vector<char> choose_big(const HostScene &hs)
   return big;
 }
 
-int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
+int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard *shard, rtb_scene **out)
 {
   const bool all_trees = (flags & RTB_SCENE_ALL_TREES) != 0;
   int ndev = 0;
@@ -789,7 +790,16 @@ int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
   RTB_CUDA(cudaSetDevice(device));
   RTB_CUDA(pool_setup(device));
 
-  cudaEvent_t ev0, ev1;
+  struct EventPair /* destroyed on every return path */
+  {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair()
+    {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } evp;
+  cudaEvent_t &ev0 = evp.a, &ev1 = evp.b;
   RTB_CUDA(cudaEventCreate(&ev0));
   RTB_CUDA(cudaEventCreate(&ev1));
   RTB_CUDA(cudaEventRecord(ev0, 0));
@@ -877,12 +887,20 @@ int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
   {
     const int T = 256;
     const int blocks = (int)((N + T - 1) / T);
-    RTB_CUDA(d_unsorted.alloc(N));
-    RTB_CUDA(d_lo.alloc(N));
-    RTB_CUDA(d_hi.alloc(N));
+    /* Sharded upload (rtb_multi.cu): with G ranks on one box every rank uploads and marshals only its
+     * 1/G of the triangles (120 B each over PCIe) and the marshalled records (104 B each) are
+     * all-gathered over NVLink, instead of every GPU pulling the whole mesh through its own PCIe link.
+     * The arrays are padded to G equal chunks so the gather can run in place. */
+    const bool sharded = shard != nullptr && shard->n_ranks > 1 && n_tris >= (size_t)shard->n_ranks * 4096;
+    const size_t G = sharded ? (size_t)shard->n_ranks : 1;
+    const size_t tri_chunk = (n_tris + G - 1) / G;
+    const size_t N_alloc = n_bs + tri_chunk * G;
+    RTB_CUDA(d_unsorted.alloc(N_alloc));
+    RTB_CUDA(d_lo.alloc(N_alloc));
+    RTB_CUDA(d_hi.alloc(N_alloc));
     if (want_tex)
     {
-      RTB_CUDA(d_tex_unsorted.alloc(3 * N));
+      RTB_CUDA(d_tex_unsorted.alloc(3 * N_alloc));
       if (n_bs)
         RTB_CUDA(cudaMemsetAsync(d_tex_unsorted.p, 0, sizeof(float2) * 3 * n_bs, 0));
     }
@@ -897,24 +915,43 @@ int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
       /* raw Vertex arrays go up as they are (120 B per triangle) and are converted on the
        * device; staging is bounded so huge meshes do not double their footprint */
       const size_t chunk_tris = 1u << 21;
-      size_t max_chunk = 0;
-      for (const MeshRange &m : hs.meshes)
-        max_chunk = std::max(max_chunk, std::min(chunk_tris, m.n_tris));
-      if (max_chunk)
-        RTB_CUDA(d_stage.alloc(3 * max_chunk));
-      size_t offset = n_bs;
+      /* this rank's share of the concatenated triangle list: everything, or chunk `rank` of G */
+      const size_t my_first = sharded ? std::min(n_tris, tri_chunk * (size_t)shard->rank) : 0;
+      const size_t my_end = sharded ? std::min(n_tris, my_first + tri_chunk) : n_tris;
+      size_t max_chunk = 0, tri_first = 0;
       for (const MeshRange &m : hs.meshes)
       {
-        for (size_t t0 = 0; t0 < m.n_tris; t0 += chunk_tris)
+        const size_t lo = std::max(tri_first, my_first), hi = std::min(tri_first + m.n_tris, my_end);
+        if (hi > lo)
+          max_chunk = std::max(max_chunk, std::min(chunk_tris, hi - lo));
+        tri_first += m.n_tris;
+      }
+      if (max_chunk)
+        RTB_CUDA(d_stage.alloc(3 * max_chunk));
+      tri_first = 0;
+      for (const MeshRange &m : hs.meshes)
+      {
+        const size_t lo = std::max(tri_first, my_first), hi = std::min(tri_first + m.n_tris, my_end);
+        for (size_t g0 = lo; g0 < hi; g0 += chunk_tris)
         {
-          size_t cnt = std::min(chunk_tris, m.n_tris - t0);
+          const size_t cnt = std::min(chunk_tris, hi - g0);
+          const size_t t0 = g0 - tri_first;    /* first triangle of the piece inside its mesh */
+          const size_t offset = n_bs + g0;     /* its slot in the (unsorted) primitive arrays */
           RTB_CUDA(cudaMemcpyAsync(d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, cudaMemcpyHostToDevice, 0));
           k_marshal_tris<<<(int)((cnt + T - 1) / T), T>>>(d_stage.p, (int)cnt, m.obj, (int)(m.gid_first + (long long)t0),
                                                           d_unsorted.p + offset, d_lo.p + offset, d_hi.p + offset,
                                                           want_tex ? d_tex_unsorted.p + 3 * offset : nullptr);
           RTB_CUDA(cudaGetLastError());
-          offset += cnt;
         }
+        tri_first += m.n_tris;
+      }
+      if (sharded)
+      {
+        int grc = rtb_shard_allgather(shard, d_unsorted.p + n_bs, sizeof(PrimRec) * tri_chunk, d_lo.p + n_bs, d_hi.p + n_bs,
+                                      sizeof(float4) * tri_chunk, want_tex ? d_tex_unsorted.p + 3 * n_bs : nullptr,
+                                      sizeof(float2) * 3 * tri_chunk);
+        if (grc != RTB_OK)
+          return grc;
       }
     }
 
@@ -1032,8 +1069,6 @@ int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
   RTB_CUDA(cudaEventSynchronize(ev1)); /* the only host wait of the build */
   float ms = 0;
   RTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
 
   if (N > 0)
   {
@@ -1062,7 +1097,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, rtb_scene **out)
      * fits: such a scene is rendered with the BVH2 walk (same results, see SceneView::nodes4q) */
     bvh4_ok = 3 * depth4 <= RTB_STACK_SIZE - 2;
     if (!bvh4_ok && !all_trees)
-      return build_scene(hs, device, flags | RTB_SCENE_ALL_TREES, out); /* rare: build the BVH2 as well */
+      return build_scene(hs, device, flags | RTB_SCENE_ALL_TREES, shard, out); /* rare: build the BVH2 as well */
   }
 
   view.nodes = sc->d_nodes;
@@ -1112,7 +1147,7 @@ extern "C" int rtb_scene_create_flags(const void *scene_objects96, size_t n_obje
   int rc = gather_scene_objects(static_cast<const RefSceneObject *>(scene_objects96), n_objects, hs);
   if (rc != RTB_OK)
     return rc;
-  return build_scene(hs, device, flags, out);
+  return build_scene(hs, device, flags, nullptr, out);
 }
 
 extern "C" int rtb_scene_create_objects_flags(const void *objects88, size_t n_objects, int device, unsigned flags,
@@ -1138,7 +1173,43 @@ extern "C" int rtb_scene_create_objects_flags(const void *objects88, size_t n_ob
     push_material(hs, objs[i].flags, objs[i].color, objs[i].emission);
     hs.spheres.push_back(SphereIn{ objs[i].center.x, objs[i].center.y, objs[i].center.z, objs[i].radius, (int)i, (int)i });
   }
-  return build_scene(hs, device, flags, out);
+  return build_scene(hs, device, flags, nullptr, out);
+}
+
+/* rtb_multi.cu: the collective form of rtb_scene_create*; kind = 88 (Object) or 96 (SceneObject) */
+int rtb_scene_create_sharded(const void *objects, size_t n_objects, int kind, int device, unsigned flags,
+                             const rtb_scene_shard *shard, rtb_scene **out)
+{
+  if (!out || (n_objects && !objects) || (kind != 88 && kind != 96))
+  {
+    rtb_set_error("rtb_scene_create_sharded: bad argument");
+    return RTB_EINVAL;
+  }
+  *out = nullptr;
+  HostScene hs;
+  if (kind == 96)
+  {
+    int rc = gather_scene_objects(static_cast<const RefSceneObject *>(objects), n_objects, hs);
+    if (rc != RTB_OK)
+      return rc;
+  }
+  else
+  {
+    if (n_objects >= (1ull << 27))
+    {
+      rtb_set_error("scene too large (>= 2^27 primitives)");
+      return RTB_EINVAL;
+    }
+    const RefObject *objs = static_cast<const RefObject *>(objects);
+    hs.n_objects = n_objects;
+    hs.n_prims = (long long)n_objects;
+    for (size_t i = 0; i < n_objects; i++)
+    {
+      push_material(hs, objs[i].flags, objs[i].color, objs[i].emission);
+      hs.spheres.push_back(SphereIn{ objs[i].center.x, objs[i].center.y, objs[i].center.z, objs[i].radius, (int)i, (int)i });
+    }
+  }
+  return build_scene(hs, device, flags, shard, out);
 }
 
 extern "C" int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info)

@@ -48,22 +48,7 @@ struct WfQueue
   double2 *d_yz;  /* direction.y, direction.z */
   uint4 *path;    /* path slot id, throughput r, g, b (float bits) */
   uint4 *hit;     /* best.t (two words), gid, slot */
-  float4 *rf0;    /* FP32 walk set-up made by the producer: 1/d.x, 1/d.y, 1/d.z, walk bound tmax */
-  float4 *rf1;    /* (re-based origin) / d per axis, parametric offset t_base (< 0: the ray needs no walk) */
 };
-
-/* the FP32 view the walk needs (rayf_walk_setup, rtb_device.cuh), computed where the ray is made */
-__device__ __forceinline__ void wf_pack_walk(const SceneView &sv, const d3 &o, const d3 &d, const HitRec &seed,
-                                             float4 &rf0, float4 &rf1)
-{
-  RayF rf;
-  rayf_basic(o, d, rf);
-  rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = 0.0f;
-  rf.t_base = 0.0f;
-  const bool walk = rayf_walk_setup(sv, o, d, seed, rf) && sv.root_ref != RTB_REF_NONE;
-  rf0 = make_float4(rf.idx, rf.idy, rf.idz, rf.tmax);
-  rf1 = make_float4(rf.oodx, rf.oody, rf.oodz, walk ? rf.t_base : -1.0f);
-}
 
 
 __device__ __forceinline__ uint4 pack_hit(const HitRec &h)
@@ -145,7 +130,7 @@ __device__ __forceinline__ unsigned ray_sort_key(const SceneView &sv, const d3 &
 }
 
 /* warp-aggregated append: every lane of the warp must call this */
-__device__ __forceinline__ void wf_enqueue(const SceneView &sv, const WfQueue &q, unsigned *count, bool want, int lane, const d3 &o, const d3 &d,
+__device__ __forceinline__ void wf_enqueue(const WfQueue &q, unsigned *count, bool want, int lane, const d3 &o, const d3 &d,
                                            unsigned pid, float tr, float tg, float tb, const HitRec &seed,
                                            unsigned *keys = nullptr, unsigned key = 0u)
 {
@@ -166,10 +151,6 @@ __device__ __forceinline__ void wf_enqueue(const SceneView &sv, const WfQueue &q
     __stcs(q.d_yz + i, make_double2(d.y, d.z));
     __stcs(q.path + i, make_uint4(pid, __float_as_uint(tr), __float_as_uint(tg), __float_as_uint(tb)));
     __stcs(q.hit + i, pack_hit(seed));
-    float4 rf0, rf1;
-    wf_pack_walk(sv, o, d, seed, rf0, rf1);
-    __stcs(q.rf0 + i, rf0);
-    __stcs(q.rf1 + i, rf1);
     if (keys)
       __stcs(keys + i, key);
   }
@@ -236,10 +217,6 @@ __global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ 
     __stcs(q.d_yz + i, make_double2(st.d.y, st.d.z));
     __stcs(q.path + i, make_uint4(pid, __float_as_uint(st.tr), __float_as_uint(st.tg), __float_as_uint(st.tb)));
     __stcs(q.hit + i, pack_hit(seed));
-    float4 rf0, rf1;
-    wf_pack_walk(A.sv, st.o, st.d, seed, rf0, rf1);
-    __stcs(q.rf0 + i, rf0);
-    __stcs(q.rf1 + i, rf1);
   }
   for (int off = 16; off > 0; off >>= 1)
     exact += __shfl_xor_sync(WF_FULL, exact, off);
@@ -270,11 +247,9 @@ __global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ 
  * 2 = streaming (evict-first) loads/stores for queue data; 4 = whole traversal stack in local
  * memory (no shared-memory top); 8 = BVH4 (128-byte nodes, rtb_internal.h); 16 = compressed BVH4 (64-byte nodes);
  * 32 / 64 = with 16: 6 / 12 of the 24 plane-byte conversions of a node on the ALU + FMA pipes instead of
- * the conversion pipe; 128 = pops read the top two stack entries at once; 256 = the FP32 walk set-up of a
- * ray (reciprocal direction, re-based origin, walk bound: rayf_walk_setup) is read from the queue, where
- * the PRODUCER of the ray stored it with all its lanes busy, instead of being computed here by the few
- * lanes of a refill (the kernel is issue-bound at 17 of 32 lanes: every instruction moved out of a
- * low-lane section counts double). */
+ * the conversion pipe; 128 = pops read the top two stack entries at once.
+ * (Measured and removed in round 2, profiles/r2_wf_tuning.md: prefetching the next rays of the batch into
+ * L1 / L2 after every refill; reading the FP32 walk set-up from the queue, written by the producer.) */
 template <int V> struct WfTraceCfg { static constexpr int blocks = (V & 1) ? 10 : 8; static constexpr int sd = (V & 4) ? 0 : WF_SMEM_STACK; };
 
 __device__ __forceinline__ double2 wf_ld(const double2 *p, bool stream)
@@ -294,7 +269,6 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
   constexpr bool RELOAD = (V & 1) != 0, STREAM = (V & 2) != 0;
   constexpr int WIDE = (V & 16) ? (2 + ((V >> 5) & 3)) : ((V & 8) ? 1 : 0);
   constexpr bool POP2 = (V & 128) != 0;
-  constexpr bool PRESET = (V & 256) != 0;
   constexpr int SD = WfTraceCfg<V>::sd;
   __shared__ int2 s_stack[SD > 0 ? SD : 1][128];
   const int lane = threadIdx.x & 31;
@@ -350,20 +324,8 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         const double2 a = wf_ld(q.o_xy + ray, STREAM), b = wf_ld(q.oz_dx + ray, STREAM), c = wf_ld(q.d_yz + ray, STREAM);
         d3 o_ = d3_make(a.x, a.y, b.x), d_ = d3_make(b.y, c.x, c.y);
         best = unpack_hit(wf_ld(q.hit + ray, STREAM));
-        bool walk;
-        if (PRESET)
-        {
-          const float4 r0 = __ldcs(q.rf0 + ray), r1 = __ldcs(q.rf1 + ray);
-          rf.idx = r0.x; rf.idy = r0.y; rf.idz = r0.z; rf.tmax = r0.w;
-          rf.oodx = r1.x; rf.oody = r1.y; rf.oodz = r1.z; rf.t_base = r1.w;
-          walk = r1.w >= 0.0f;
-        }
-        else
-        {
-          rayf_basic(o_, d_, rf);
-          walk = rayf_walk_setup(sv, o_, d_, best, rf);
-        }
-        if (walk)
+        rayf_basic(o_, d_, rf);
+        if (rayf_walk_setup(sv, o_, d_, best, rf))
         {
           stack.reset();
           cur = sv.root_ref;
@@ -517,7 +479,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_BLOCKS) k_wf_shade(const __grid_
       if (st.alive)
         ray_seed_hit(A.sv, st.o, st.d, seed, exact);
     }
-    wf_enqueue(A.sv, qout, n_out, st.alive, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed, keys_out,
+    wf_enqueue(qout, n_out, st.alive, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed, keys_out,
                (keys_out && st.alive) ? ray_sort_key(A.sv, st.o, st.d, sort_mode) : 0u);
   }
   wf_add_counters(A.counters, lane, pc.rays, pc.rays_hit, exact, 0ull, 0ull);
@@ -582,7 +544,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   const int sort_from = 1;                                           /* primary rays are coherent already */
   const int sort_until = (desc->reserved2 >> 8) & 0xFF ? (desc->reserved2 >> 8) & 0xFF : 255;
 
-  /* one allocation: 2 queues x 7 arrays of 16 B, the planes, sort buffers, the per-wave counters */
+  /* one allocation: 2 queues x 5 arrays of 16 B, the planes, sort buffers, the per-wave counters */
   const size_t arr = align_up(slots * 16, 256);
   const size_t arr4 = align_up(slots * 4, 256);
   const size_t ctr_bytes = align_up(sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), 256);
@@ -593,7 +555,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, nul, nul, nul, nul, (int)slots, 0, 24, stream);
     sort_tmp_bytes = align_up(sort_tmp_bytes, 256);
   }
-  const size_t need = arr * 15 + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0);
+  const size_t need = arr * 11 + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0);
   if (scene->wf_bytes < need)
   {
     if (scene->d_wf)
@@ -630,8 +592,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     q[k].d_yz = reinterpret_cast<double2 *>(p); p += arr;
     q[k].path = reinterpret_cast<uint4 *>(p); p += arr;
     q[k].hit = reinterpret_cast<uint4 *>(p); p += arr;
-    q[k].rf0 = reinterpret_cast<float4 *>(p); p += arr;
-    q[k].rf1 = reinterpret_cast<float4 *>(p); p += arr;
   }
   float4 *planes = reinterpret_cast<float4 *>(p); p += arr;
   unsigned *counts = reinterpret_cast<unsigned *>(p);            /* [n_bounces + 2] queue lengths */
@@ -659,7 +619,14 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   const int gen_blocks = (int)((gen_warps * 32 + 255) / 256);
 
   /* per-kernel timing (only with counters): events around every trace launch */
-  std::vector<cudaEvent_t> ev;
+  struct EventList : std::vector<cudaEvent_t> /* destroyed on every return path */
+  {
+    ~EventList()
+    {
+      for (cudaEvent_t e : *this)
+        cudaEventDestroy(e);
+    }
+  } ev;
   auto mark = [&]() {
     if (!phase_ms)
       return;
@@ -689,8 +656,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       case 4: launch_trace<4>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 18: launch_trace<18>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 22: launch_trace<22>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 279: launch_trace<279>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 278: launch_trace<278>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 54: launch_trace<54>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 86: launch_trace<86>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 150: launch_trace<150>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
@@ -735,8 +700,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     phase_ms[0] = trace;
     phase_ms[1] = total - trace; /* generate of later waves + shade + sum (the first generate is before ev[0]) */
     phase_ms[2] = (float)(ev.size() / 2);
-    for (cudaEvent_t e : ev)
-      cudaEventDestroy(e);
   }
   return RTB_OK;
 }

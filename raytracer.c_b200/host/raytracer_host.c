@@ -12,6 +12,7 @@
  * conveniences for host code, not a rendering fallback.
  */
 #include <time.h>
+#include <stdlib.h>
 
 #include "raytracer.h"
 #include "rtb200.h"
@@ -146,6 +147,11 @@ void render_params_default(RenderParams *p)
   p->device = 0;
   p->accum_out = NULL;
   p->integrator = RT_INTEGRATOR_PATH;
+  /* the unchanged main.c calls render() without parameters: RTB_NUM_GPUS lets it use the whole box */
+  const char *env = getenv("RTB_NUM_GPUS");
+  p->num_gpus = env ? atoi(env) : 1;
+  if (p->num_gpus < 1)
+    p->num_gpus = 1;
 }
 
 static void die(const char *where)
@@ -154,8 +160,60 @@ static void die(const char *where)
   exit(EXIT_FAILURE);
 }
 
-static void render_on_scene(uint8_t *framebuffer, rtb_scene *scene, Camera *camera, Options *options,
-                            const RenderParams *params)
+/* mesh placement helper of the reference's driver (main.c:140-147): every vertex position through
+ * mat4_vector_mult (vector.h:63-74), in double.  The transformed positions are in general no longer
+ * float-representable; the scene upload keeps them in double for the exact triangle test. */
+void apply_matrix(TriangleMesh *mesh, mat4 matrix)
+{
+  for (size_t i = 0; i < mesh->num_triangles * 3; i++)
+    mesh->vertices[i].pos = mat4_vector_mult(matrix, mesh->vertices[i].pos);
+}
+
+static void fill_desc(rtb_render_desc *desc, const Options *options, const RenderParams *p)
+{
+  memset(desc, 0, sizeof(*desc));
+  desc->width = options->width;
+  desc->height = options->height;
+  desc->sample_begin = p->sample_offset;
+  desc->sample_end = p->sample_offset + options->samples;
+  desc->max_depth = p->max_depth;
+  desc->dielectric_mode = p->dielectric_mode == RT_DIELECTRIC_SPLIT ? RTB_DIELECTRIC_SPLIT : RTB_DIELECTRIC_STOCHASTIC;
+  desc->seed = p->seed;
+  desc->integrator = p->integrator == RT_INTEGRATOR_WHITTED ? RTB_INTEGRATOR_WHITTED : RTB_INTEGRATOR_PATH;
+}
+
+/* One comm per process and GPU count, made on first use (NCCL communicator set-up costs ~0.1-1 s) and
+ * kept: render() is called once per frame by the reference's driver, a viewer would call it per frame. */
+static rtb_comm *g_comm = NULL;
+static int g_comm_gpus = 0;
+
+static void drop_comm(void)
+{
+  if (g_comm)
+    rtb_comm_destroy(g_comm);
+  g_comm = NULL;
+}
+
+static rtb_comm *local_comm(int num_gpus)
+{
+  if (g_comm && g_comm_gpus == num_gpus)
+    return g_comm;
+  static int registered = 0;
+  drop_comm();
+  if (rtb_comm_create_local(NULL, num_gpus, &g_comm) != RTB_OK)
+    die("render: multi-GPU set-up");
+  g_comm_gpus = num_gpus;
+  if (!registered)
+  {
+    atexit(drop_comm);
+    registered = 1;
+  }
+  return g_comm;
+}
+
+/* the body of render(): objects are Object (88-byte) or SceneObject (96-byte) records */
+static void render_records(uint8_t *framebuffer, const void *objects, size_t n_objects, int record_bytes,
+                           Camera *camera, Options *options, const RenderParams *params)
 {
   RenderParams p;
   if (params)
@@ -164,24 +222,49 @@ static void render_on_scene(uint8_t *framebuffer, rtb_scene *scene, Camera *came
     render_params_default(&p);
   if (p.max_depth < 0)
     p.max_depth = MAX_DEPTH;
+  if (p.num_gpus < 1)
+    p.num_gpus = 1;
 
   rtb_render_desc desc;
-  memset(&desc, 0, sizeof(desc));
-  desc.width = options->width;
-  desc.height = options->height;
-  desc.sample_begin = p.sample_offset;
-  desc.sample_end = p.sample_offset + options->samples;
-  desc.max_depth = p.max_depth;
-  desc.dielectric_mode = RTB_DIELECTRIC_STOCHASTIC;
-  desc.seed = p.seed;
-  desc.integrator = p.integrator == RT_INTEGRATOR_WHITTED ? RTB_INTEGRATOR_WHITTED : RTB_INTEGRATOR_PATH;
-
+  fill_desc(&desc, options, &p);
   const double *cam = (const double *)camera; /* 12 doubles, raytracer.h:121-124 */
+  const int divisor = p.total_samples > 0 ? p.total_samples : options->samples;
   rtb_counters counters;
-  if (rtb_render(scene, cam, &desc, framebuffer, p.accum_out, &counters) != RTB_OK)
+
+  if (p.num_gpus > 1)
   {
+    /* all GPUs of the box: spp-sharded, one ncclReduce of the float sums (rtb200.h) */
+    if (p.total_samples > 0 && p.total_samples != options->samples)
+    {
+      fprintf(stderr, "render: total_samples is for a caller that shards samples itself; with num_gpus > 1 the library does\n");
+      exit(EXIT_FAILURE);
+    }
+    if (rtb_render_multi(local_comm(p.num_gpus), objects, n_objects, record_bytes, cam, &desc, framebuffer, p.accum_out,
+                         &counters) != RTB_OK)
+      die("render");
+  }
+  else
+  {
+    rtb_scene *scene = NULL;
+    const int timing = getenv("RTB_TIMING") != NULL; /* development aid: where an end-to-end call spends its time */
+    struct timespec t0, t1, t2;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    int rc = record_bytes == 96 ? rtb_scene_create(objects, n_objects, p.device, &scene)
+                                : rtb_scene_create_objects(objects, n_objects, p.device, &scene);
+    if (rc != RTB_OK)
+      die("render: scene upload");
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (rtb_render_mean(scene, cam, &desc, divisor, framebuffer, p.accum_out, &counters) != RTB_OK)
+    {
+      rtb_scene_destroy(scene);
+      die("render");
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t2);
     rtb_scene_destroy(scene);
-    die("render");
+    if (timing)
+      fprintf(stderr, "render: create %.1f ms, render %.1f ms\n",
+              1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec),
+              1e3 * (double)(t2.tv_sec - t1.tv_sec) + 1e-6 * (double)(t2.tv_nsec - t1.tv_nsec));
   }
   /* same meaning as the reference's globals (raytracer.c:36-37) */
   ray_count += (long long)counters.rays;
@@ -191,12 +274,7 @@ static void render_on_scene(uint8_t *framebuffer, rtb_scene *scene, Camera *came
 void render_ex(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *camera, Options *options,
                const RenderParams *params)
 {
-  rtb_scene *scene = NULL;
-  int device = params ? params->device : 0;
-  if (rtb_scene_create_objects(objects, n_objects, device, &scene) != RTB_OK)
-    die("render: scene upload");
-  render_on_scene(framebuffer, scene, camera, options, params);
-  rtb_scene_destroy(scene);
+  render_records(framebuffer, objects, n_objects, 88, camera, options, params);
 }
 
 void render(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *camera, Options *options)
@@ -204,27 +282,8 @@ void render(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *cam
   render_ex(framebuffer, objects, n_objects, camera, options, NULL);
 }
 
-static double now_ms(void)
-{
-  struct timespec t;
-  clock_gettime(CLOCK_MONOTONIC, &t);
-  return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
-}
-
 void render_scene(uint8_t *framebuffer, SceneObject *objects, size_t n_objects, Camera *camera,
                   Options *options, const RenderParams *params)
 {
-  rtb_scene *scene = NULL;
-  int device = params ? params->device : 0;
-  const int timing = getenv("RTB_TIMING") != NULL; /* development aid: where an end-to-end call spends its time */
-  double t0 = now_ms();
-  if (rtb_scene_create(objects, n_objects, device, &scene) != RTB_OK)
-    die("render_scene: scene upload");
-  double t1 = now_ms();
-  render_on_scene(framebuffer, scene, camera, options, params);
-  double t2 = now_ms();
-  rtb_scene_destroy(scene);
-  double t3 = now_ms();
-  if (timing)
-    fprintf(stderr, "render_scene: create %.1f ms, render %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2);
+  render_records(framebuffer, objects, n_objects, 96, camera, options, params);
 }

@@ -231,22 +231,29 @@ def test_cli_usage_and_errors():
     assert r.returncode != 0
 
 
-# ---- multi-GPU sharding (gloo, world_size 2) -----------------------------------------------------------
+# ---- multi-GPU host logic (gloo, world_size 2) ---------------------------------------------------------
+# The multi-GPU data path lives behind the C ABI (rtb_comm_*, csrc/rtb_multi.cu): sample ranges per rank,
+# ncclReduce, tonemap on rank 0.  What can run without a GPU is its host logic: the shard arithmetic
+# (rtb_comm_shard_samples) and the launcher-side plumbing bench.py uses -- rank 0's 128-byte id reaches
+# every rank through torch.distributed, every rank derives its own sample range from the same job.
 
 def test_shard_ranges(pkg):
-    sh = pkg.sharding
-    assert sh.shard_weak(0, 8, 512) == (0, 512, 4096) and sh.shard_weak(7, 8, 512) == (3584, 4096, 4096)
-    got = [sh.shard_strong(r, 3, 128) for r in range(3)]
+    api = pkg.api
+    assert api.shard_samples(0, 4096, 0, 8) == (0, 512) and api.shard_samples(0, 4096, 7, 8) == (3584, 4096)
+    got = [api.shard_samples(0, 128, r, 3) for r in range(3)]
     assert got[0][0] == 0 and got[-1][1] == 128 and all(a[1] == b[0] for a, b in zip(got, got[1:]))
-    assert sorted(e - b for b, e, _ in got) == [42, 43, 43]
-    for world in (1, 2, 4, 8):
-        cover = []
-        for r in range(world):
-            b, e, tot = sh.shard_strong(r, world, 4096)
-            cover += list(range(b, e))
-        assert cover == list(range(4096))
-    with pytest.raises(ValueError):
-        sh.shard_weak(2, 2, 4)
+    assert sorted(e - b for b, e in got) == [42, 43, 43]
+    for world in (1, 2, 3, 4, 8):
+        for begin, end in ((0, 4096), (7, 7 + 128), (5, 5), (0, 3)):  # also fewer samples than ranks
+            cover = []
+            for r in range(world):
+                b, e = api.shard_samples(begin, end, r, world)
+                cover += list(range(b, e))
+            assert cover == list(range(begin, end))
+    with pytest.raises(api.RtbError):
+        api.shard_samples(0, 4, 2, 2)
+    with pytest.raises(api.RtbError):
+        api.shard_samples(4, 0, 0, 2)
 
 
 _WORKER = r"""
@@ -255,24 +262,32 @@ sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
 import __graft_entry__ as entry
 pkg = entry.load_package()
+api = pkg.api
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
-W, H, spp = 16, 8, 4
-b, e, total = pkg.sharding.shard_weak(rank, world, spp)
+# 1. the id travels from rank 0 to everybody (bench.py does this with the real rtb_comm_unique_id)
+idt = torch.zeros(api.UNIQUE_ID_BYTES, dtype=torch.uint8)
+if rank == 0:
+    idt.copy_(torch.frombuffer(bytearray(bytes(range(128))), dtype=torch.uint8))
+dist.broadcast(idt, src=0)
+assert bytes(idt.numpy().tobytes()) == bytes(range(128))
+# 2. every rank derives its share of the SAME job through the C ABI
+W, H, begin, end = 16, 8, 3, 3 + 9
+b, e = api.shard_samples(begin, end, rank, world)
 # stand-in for the per-GPU float sums: sample s contributes (s+1) to every pixel
 accum = torch.full((H, W, 3), float(sum(s + 1 for s in range(b, e))), dtype=torch.float32)
-pkg.sharding.reduce_to_root(accum, world)
+dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)   # gloo standing in for the ncclReduce of rtb_comm_render
 if rank == 0:
-    want = float(sum(s + 1 for s in range(total)))
-    assert total == world * spp and torch.all(accum == want), (accum[0, 0], want)
-    print("OK", total, want)
+    want = float(sum(s + 1 for s in range(begin, end)))
+    assert torch.all(accum == want), (accum[0, 0], want)
+    print("OK", e - b, want)
 dist.barrier()
 dist.destroy_process_group()
 """
 
 
-def test_two_rank_reduce_over_gloo(tmp_path):
-    """the N>1 host logic: disjoint global sample ranges per rank, one SUM reduce to rank 0"""
+def test_two_rank_job_over_gloo(tmp_path):
+    """the N>1 host logic: id broadcast, disjoint covering sample ranges per rank, one SUM reduce to rank 0"""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=ROOT))
     port = 29500 + (os.getpid() % 2000)
@@ -280,4 +295,22 @@ def test_two_rank_reduce_over_gloo(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
-    assert "OK 8 36.0" in r.stdout
+    assert "OK 4 72.0" in r.stdout
+
+
+def test_render_params_carry_num_gpus(pkg):
+    """RenderParams.num_gpus defaults to 1, or to $RTB_NUM_GPUS (how the unchanged main.c gets the whole box)"""
+    import ctypes as C
+    _, host = pkg.load()
+    rp = pkg.abi.RenderParams()
+    old = os.environ.pop("RTB_NUM_GPUS", None)
+    try:
+        host.render_params_default(C.byref(rp))
+        assert rp.num_gpus == 1 and rp.total_samples == 0 and rp.max_depth == 5
+        os.environ["RTB_NUM_GPUS"] = "8"
+        host.render_params_default(C.byref(rp))
+        assert rp.num_gpus == 8
+    finally:
+        os.environ.pop("RTB_NUM_GPUS", None)
+        if old is not None:
+            os.environ["RTB_NUM_GPUS"] = old
