@@ -362,10 +362,34 @@ class Scene:
 UNIQUE_ID_BYTES = 128
 
 
+_nccl_preloaded = False
+
+
+def _prefer_bundled_nccl():
+    """librtb200.so binds libnccl.so.2 with dlopen on first use (a copy already in the process wins).  In a
+    Python process PyTorch may be imported LATER and needs its own, newer NCCL under the same soname: load
+    that copy first, so both sides share it whatever the import order.  A C caller gets the system's."""
+    global _nccl_preloaded
+    if _nccl_preloaded or os.environ.get("RTB_NCCL_LIB"):
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except (ImportError, OSError, AttributeError):
+        pass
+
+
 def comm_unique_id():
     """rank 0 of a one-process-per-GPU job: the 128-byte id the other ranks need (send it through the
     launcher's own channel, e.g. torch.distributed.broadcast)"""
     cu, _ = load()
+    _prefer_bundled_nccl()
     buf = (C.c_ubyte * UNIQUE_ID_BYTES)()
     _check(cu.rtb_comm_unique_id(buf), "rtb_comm_unique_id")
     return bytes(buf)
@@ -401,6 +425,7 @@ class Comm:
     @classmethod
     def rank(cls, unique_id, rank, n_ranks, device):
         cu, _ = load()
+        _prefer_bundled_nccl()
         h = C.c_void_p()
         buf = (C.c_ubyte * UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         _check(cu.rtb_comm_create_rank(buf, rank, n_ranks, device, C.byref(h)), "rtb_comm_create_rank")
@@ -409,6 +434,7 @@ class Comm:
     @classmethod
     def local(cls, n_devices, devices=None):
         cu, _ = load()
+        _prefer_bundled_nccl()
         h = C.c_void_p()
         arr = (C.c_int * n_devices)(*devices) if devices is not None else None
         _check(cu.rtb_comm_create_local(arr, n_devices, C.byref(h)), "rtb_comm_create_local")

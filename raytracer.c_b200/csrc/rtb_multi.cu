@@ -21,9 +21,12 @@
  */
 #include "rtb_internal.h"
 
-#include <nccl.h>
+#include <nccl.h> /* types and prototypes only: the library is bound at run time, see nccl_api() */
+
+#include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -31,13 +34,88 @@
 
 static_assert(RTB_UNIQUE_ID_BYTES == sizeof(ncclUniqueId), "rtb200.h: RTB_UNIQUE_ID_BYTES must be sizeof(ncclUniqueId)");
 
+/* NCCL is bound with dlopen on first use, not at link time, for two reasons: single-GPU callers need no
+ * NCCL at all, and a process may already hold a libnccl.so.2 (PyTorch bundles its own, newer than the
+ * system's): a link-time dependency would pull the system copy in first and break the later
+ * `import torch` (same soname, missing symbols).  Order: $RTB_NCCL_LIB, a copy already loaded in the
+ * process, then the system's libnccl.so.2.  Only entry points that exist since NCCL 2.4 are used. */
+namespace
+{
+struct NcclApi
+{
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclReduce) Reduce = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+  std::string error;
+};
+
+const NcclApi &nccl_api()
+{
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void *h = nullptr;
+    if (const char *path = getenv("RTB_NCCL_LIB"))
+      h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+      h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+    if (!h)
+      h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+    {
+      api.error = std::string("libnccl.so.2 not found: ") + dlerror();
+      return;
+    }
+    bool all = true;
+    auto bind = [&](auto &fn, const char *name) {
+      fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name));
+      if (!fn)
+      {
+        all = false;
+        api.error = std::string("libnccl.so.2 lacks ") + name;
+      }
+    };
+    bind(api.GetUniqueId, "ncclGetUniqueId");
+    bind(api.CommInitRank, "ncclCommInitRank");
+    bind(api.CommInitAll, "ncclCommInitAll");
+    bind(api.CommDestroy, "ncclCommDestroy");
+    bind(api.AllGather, "ncclAllGather");
+    bind(api.AllReduce, "ncclAllReduce");
+    bind(api.Reduce, "ncclReduce");
+    bind(api.GroupStart, "ncclGroupStart");
+    bind(api.GroupEnd, "ncclGroupEnd");
+    bind(api.GetErrorString, "ncclGetErrorString");
+    api.ok = all;
+  });
+  return api;
+}
+} // namespace
+
+#define RTB_NEED_NCCL()                                                                        \
+  do                                                                                           \
+  {                                                                                            \
+    if (!nccl_api().ok)                                                                        \
+    {                                                                                          \
+      rtb_set_error("multi-GPU entry points need NCCL: " + nccl_api().error);                  \
+      return RTB_ECUDA;                                                                        \
+    }                                                                                          \
+  } while (0)
+
 #define RTB_NCCL(call)                                                                         \
   do                                                                                           \
   {                                                                                            \
     ncclResult_t r_ = (call);                                                                  \
     if (r_ != ncclSuccess)                                                                     \
     {                                                                                          \
-      rtb_set_error(std::string(#call) + ": " + ncclGetErrorString(r_));                       \
+      rtb_set_error(std::string(#call) + ": " + nccl_api().GetErrorString(r_));                       \
       return RTB_ECUDA;                                                                        \
     }                                                                                          \
   } while (0)
@@ -65,8 +143,9 @@ extern "C" int rtb_comm_unique_id(void *id128)
     rtb_set_error("rtb_comm_unique_id: NULL argument");
     return RTB_EINVAL;
   }
+  RTB_NEED_NCCL();
   ncclUniqueId id;
-  RTB_NCCL(ncclGetUniqueId(&id));
+  RTB_NCCL(nccl_api().GetUniqueId(&id));
   memcpy(id128, &id, sizeof(id));
   return RTB_OK;
 }
@@ -79,13 +158,14 @@ extern "C" int rtb_comm_create_rank(const void *id128, int rank, int n_ranks, in
     return RTB_EINVAL;
   }
   *out = nullptr;
+  RTB_NEED_NCCL();
   RTB_CUDA(cudaSetDevice(device));
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   RankCtx r;
   r.rank = rank;
   r.device = device;
-  RTB_NCCL(ncclCommInitRank(&r.nccl, n_ranks, id, rank));
+  RTB_NCCL(nccl_api().CommInitRank(&r.nccl, n_ranks, id, rank));
   rtb_comm *c = new rtb_comm();
   c->n_ranks = n_ranks;
   c->local.push_back(r);
@@ -103,6 +183,8 @@ extern "C" int rtb_comm_create_local(const int *devices_or_null, int n_devices, 
   *out = nullptr;
   int have = 0;
   RTB_CUDA(cudaGetDeviceCount(&have));
+  if (n_devices > 1)
+    RTB_NEED_NCCL();
   std::vector<int> devs(n_devices);
   for (int k = 0; k < n_devices; k++)
   {
@@ -113,8 +195,9 @@ extern "C" int rtb_comm_create_local(const int *devices_or_null, int n_devices, 
       return RTB_EINVAL;
     }
   }
-  std::vector<ncclComm_t> comms(n_devices);
-  RTB_NCCL(ncclCommInitAll(comms.data(), n_devices, devs.data()));
+  std::vector<ncclComm_t> comms(n_devices, nullptr);
+  if (n_devices > 1) /* a group of one needs no communicator: every collective below is skipped for it */
+    RTB_NCCL(nccl_api().CommInitAll(comms.data(), n_devices, devs.data()));
   rtb_comm *c = new rtb_comm();
   c->n_ranks = n_devices;
   for (int k = 0; k < n_devices; k++)
@@ -143,7 +226,7 @@ extern "C" void rtb_comm_destroy(rtb_comm *comm)
     if (r.d_accum) cudaFree(r.d_accum);
     if (r.d_fb) cudaFree(r.d_fb);
     if (r.d_ctr) cudaFree(r.d_ctr);
-    if (r.nccl) ncclCommDestroy(r.nccl);
+    if (r.nccl && nccl_api().ok) nccl_api().CommDestroy(r.nccl);
   }
   delete comm;
 }
@@ -155,13 +238,13 @@ int rtb_shard_allgather(const rtb_scene_shard *shard, void *prims, size_t prim_c
   ncclComm_t comm = static_cast<ncclComm_t>(shard->nccl);
   const size_t r = (size_t)shard->rank;
   auto mine = [&](void *base, size_t chunk) { return static_cast<char *>(base) + r * chunk; };
-  RTB_NCCL(ncclGroupStart());
-  RTB_NCCL(ncclAllGather(mine(prims, prim_chunk_bytes), prims, prim_chunk_bytes, ncclChar, comm, 0));
-  RTB_NCCL(ncclAllGather(mine(box_lo, box_chunk_bytes), box_lo, box_chunk_bytes, ncclChar, comm, 0));
-  RTB_NCCL(ncclAllGather(mine(box_hi, box_chunk_bytes), box_hi, box_chunk_bytes, ncclChar, comm, 0));
+  RTB_NCCL(nccl_api().GroupStart());
+  RTB_NCCL(nccl_api().AllGather(mine(prims, prim_chunk_bytes), prims, prim_chunk_bytes, ncclChar, comm, 0));
+  RTB_NCCL(nccl_api().AllGather(mine(box_lo, box_chunk_bytes), box_lo, box_chunk_bytes, ncclChar, comm, 0));
+  RTB_NCCL(nccl_api().AllGather(mine(box_hi, box_chunk_bytes), box_hi, box_chunk_bytes, ncclChar, comm, 0));
   if (tex_or_null)
-    RTB_NCCL(ncclAllGather(mine(tex_or_null, tex_chunk_bytes), tex_or_null, tex_chunk_bytes, ncclChar, comm, 0));
-  RTB_NCCL(ncclGroupEnd());
+    RTB_NCCL(nccl_api().AllGather(mine(tex_or_null, tex_chunk_bytes), tex_or_null, tex_chunk_bytes, ncclChar, comm, 0));
+  RTB_NCCL(nccl_api().GroupEnd());
   return RTB_OK;
 }
 
@@ -232,7 +315,7 @@ static int rank_render_reduce(RankCtx &R, int n_ranks, rtb_scene *scene, const d
     return rc;
   /* the ONE collective of the data path: per-GPU float sums -> rank 0 */
   if (n_ranks > 1)
-    RTB_NCCL(ncclReduce(R.d_accum, R.d_accum, elems, ncclFloat32, ncclSum, 0, R.nccl, 0));
+    RTB_NCCL(nccl_api().Reduce(R.d_accum, R.d_accum, elems, ncclFloat32, ncclSum, 0, R.nccl, 0));
   const int total = desc->sample_end - desc->sample_begin;
   if (R.rank == 0)
   {
@@ -251,10 +334,10 @@ static int rank_render_reduce(RankCtx &R, int n_ranks, rtb_scene *scene, const d
       float *d_t = reinterpret_cast<float *>(R.d_ctr + 6);
       RTB_CUDA(cudaMemcpyAsync(R.d_ctr, h, sizeof(unsigned long long) * 6, cudaMemcpyHostToDevice, 0));
       RTB_CUDA(cudaMemcpyAsync(d_t, t, sizeof(t), cudaMemcpyHostToDevice, 0));
-      RTB_NCCL(ncclGroupStart());
-      RTB_NCCL(ncclAllReduce(R.d_ctr, R.d_ctr, 6, ncclUint64, ncclSum, R.nccl, 0));
-      RTB_NCCL(ncclAllReduce(d_t, d_t, 4, ncclFloat32, ncclMax, R.nccl, 0));
-      RTB_NCCL(ncclGroupEnd());
+      RTB_NCCL(nccl_api().GroupStart());
+      RTB_NCCL(nccl_api().AllReduce(R.d_ctr, R.d_ctr, 6, ncclUint64, ncclSum, R.nccl, 0));
+      RTB_NCCL(nccl_api().AllReduce(d_t, d_t, 4, ncclFloat32, ncclMax, R.nccl, 0));
+      RTB_NCCL(nccl_api().GroupEnd());
       RTB_CUDA(cudaMemcpyAsync(h, R.d_ctr, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, 0));
       RTB_CUDA(cudaMemcpyAsync(t, d_t, sizeof(t), cudaMemcpyDeviceToHost, 0));
       RTB_CUDA(cudaStreamSynchronize(0));
