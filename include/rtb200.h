@@ -108,6 +108,8 @@ typedef struct
   float build_ms;
   int bvh_depth;
   int device;
+  int double_triangles; /* 1: some mesh coordinate is not float-representable, the scene keeps the caller's doubles
+                           (72 B per triangle) for the exact triangle test; 0: the float records are exact */
 } rtb_scene_info;
 
 const char *rtb_last_error(void);

@@ -111,6 +111,8 @@ def _bind(cu, host):
     host.load_obj.restype = C.c_bool
     host.free_mesh.argtypes = [C.POINTER(abi.TriangleMesh)]
     host.free_mesh.restype = None
+    host.apply_matrix.argtypes = [C.POINTER(abi.TriangleMesh), C.POINTER(C.c_double)]
+    host.apply_matrix.restype = None
     host.calculate_surface_normal.argtypes = [abi.Vec3, abi.Vec3, abi.Vec3]
     host.calculate_surface_normal.restype = abi.Vec3
     host.scene_default.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -203,6 +205,18 @@ def mesh_room(verts, width, height):
     h._keep += [verts, mesh]
     h._free = [(libc, p_obj), (libc, p_sph)]
     return h
+
+
+def apply_matrix(verts, matrix):
+    """apply_matrix (main.c:140-147): every position through mat4_vector_mult, in double, in place"""
+    _, host = load()
+    assert verts.dtype == abi.VERTEX_DTYPE and verts.flags["C_CONTIGUOUS"]
+    m = np.ascontiguousarray(matrix, dtype=np.float64).reshape(16)
+    mesh = abi.TriangleMesh()
+    mesh.num_triangles = len(verts) // 3
+    mesh.vertices = C.cast(verts.ctypes.data, C.POINTER(abi.Vertex))
+    host.apply_matrix(C.byref(mesh), m.ctypes.data_as(C.POINTER(C.c_double)))
+    return verts
 
 
 def load_obj(path):

@@ -169,12 +169,30 @@ struct HitRec
   int slot; /* >= 0: index into the BVH-ordered array; < 0: ~index into the big list */
 };
 
-__device__ __forceinline__ void test_prim(const PrimView &p, int slot, const d3 &o, const d3 &d, HitRec &best)
+/* vertices of the triangle in BVH slot `slot` as the caller's own doubles (SceneView::tri64): only scenes
+ * whose mesh vertices are not float-representable carry them (apply_matrix, main.c:140-147) */
+__device__ __forceinline__ void load_tri64(const double *__restrict__ tri64, int slot, d3 &v0, d3 &v1, d3 &v2)
+{
+  const double *p = tri64 + 9 * (size_t)slot; /* 72-byte records: 8-byte aligned only */
+  v0 = d3_make(__ldg(p + 0), __ldg(p + 1), __ldg(p + 2));
+  v1 = d3_make(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5));
+  v2 = d3_make(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8));
+}
+
+/* tri64: NULL = triangle vertices are the record's floats (exact for OBJ-loaded meshes) */
+__device__ __forceinline__ void test_prim(const PrimView &p, int slot, const d3 &o, const d3 &d, HitRec &best,
+                                          const double *__restrict__ tri64 = nullptr)
 {
   double t, bu, bv;
   bool hit;
   if (p.is_sphere())
     hit = sphere_exact(o, d, p.cx(), p.cy(), p.cz(), p.radius(), t);
+  else if (tri64 != nullptr && slot >= 0)
+  {
+    d3 v0, v1, v2;
+    load_tri64(tri64, slot, v0, v1, v2);
+    hit = triangle_exact(o, d, v0, v1, v2, t, bu, bv);
+  }
   else
     hit = triangle_exact(o, d, p.v0(), p.v1(), p.v2(), t, bu, bv);
   if (hit)
@@ -232,7 +250,8 @@ __device__ __forceinline__ bool sphere_may_win(const PrimView &p, float ofx, flo
 template <bool FILTER>
 __device__ __forceinline__ void test_prim_filtered(const PrimView &p, int slot, const d3 &o, const d3 &d,
                                                    float ofx, float ofy, float ofz, float dfx, float dfy, float dfz,
-                                                   float o_abs1, HitRec &best, unsigned &exact_tests)
+                                                   float o_abs1, HitRec &best, unsigned &exact_tests,
+                                                   const double *__restrict__ tri64 = nullptr)
 {
   if (FILTER && p.is_sphere())
   {
@@ -241,7 +260,7 @@ __device__ __forceinline__ void test_prim_filtered(const PrimView &p, int slot, 
       return;
   }
   exact_tests++;
-  test_prim(p, slot, o, d, best);
+  test_prim(p, slot, o, d, best, tri64);
 }
 
 /* ---- nearest hit: big list + FP32 BVH walk with exact leaf tests ------------
@@ -598,7 +617,7 @@ __device__ __forceinline__ void closest_hit(const SceneView &sv, const d3 &o, co
         int first = code >> 3, count = (code & 7) + 1;
         for (int k = 0; k < count; k++)
           test_prim_filtered<FILTER>(load_prim(sv.prims, first + k), first + k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx,
-                             rf.dfy, rf.dfz, rf.o_abs1, best, exact);
+                             rf.dfy, rf.dfz, rf.o_abs1, best, exact, sv.tri64);
         rayf_update_tmax(rf, best);
       }
       cur = stack.pop(rf);
@@ -715,7 +734,7 @@ __device__ __forceinline__ void closest_hit_ww(const SceneView &sv, const d3 &o,
       int first = code >> 3, count = (code & 7) + 1;
       for (int k = 0; k < count; k++)
         test_prim_filtered<false>(load_prim(sv.prims, first + k), first + k, o, d, rf.ofx, rf.ofy, rf.ofz, rf.dfx,
-                                  rf.dfy, rf.dfz, rf.o_abs1, best, exact);
+                                  rf.dfy, rf.dfz, rf.o_abs1, best, exact, sv.tri64);
       rayf_update_tmax(rf, best);
       cur = stack.pop(rf);
     }
@@ -733,7 +752,7 @@ __device__ __forceinline__ void closest_hit_bruteforce(const SceneView &sv, cons
   for (int k = 0; k < sv.n_big; k++)
     test_prim(load_prim(sv.big, k), ~k, o, d, best);
   for (int k = 0; k < sv.n_prims; k++)
-    test_prim(load_prim(sv.prims, k), k, o, d, best);
+    test_prim(load_prim(sv.prims, k), k, o, d, best, sv.tri64);
 }
 
 /* ---- surface at the nearest hit (raytracer.c:406-411, :428-431) ------------- */
@@ -768,6 +787,8 @@ __device__ __forceinline__ Surface surface_at(const SceneView &sv, const d3 &o, 
   else
   {
     d3 v0 = p.v0(), v1 = p.v1(), v2 = p.v2();
+    if (sv.tri64 != nullptr && best.slot >= 0)
+      load_tri64(sv.tri64, best.slot, v0, v1, v2);
     s.normal = d3_normalize(d3_cross(d3_sub(v2, v0), d3_sub(v1, v0))); /* raytracer.c:44 */
     if (want_uv && sv.tex != nullptr && best.slot >= 0)
     {

@@ -87,6 +87,8 @@ struct SceneView
   const float4 *mats;  /* 2 float4 per object */
   const float2 *tex;   /* 3 float2 per BVH primitive (BVH order) or NULL */
   const double *colors; /* 3 doubles per object: the unscaled material colour (Whitted integrator) */
+  const double *tri64;  /* 9 doubles per BVH primitive slot: triangle vertices exactly as the caller gave them, or
+                           NULL when every mesh coordinate is float-representable (the floats of PrimRec are exact) */
   int n_prims, n_big, root_ref, n_objects;
   float guard_lo[3], guard_hi[3]; /* box rays are re-based into before FP32 traversal */
 };
@@ -100,6 +102,7 @@ struct rtb_scene
   float4 *d_nodes = nullptr, *d_prims = nullptr, *d_big = nullptr, *d_mats = nullptr;
   float2 *d_tex = nullptr;
   double *d_colors = nullptr;
+  double *d_tri64 = nullptr;
   float *d_scratch = nullptr; /* split planes */
   size_t scratch_bytes = 0;
   void *d_wf = nullptr;       /* wavefront kernels: ray queues + accumulation planes (rtb_wavefront.cu) */
@@ -130,6 +133,8 @@ struct rtb_scene_shard
  * their boxes and (optionally) texture coordinates, on the legacy default stream of the current device */
 int rtb_shard_allgather(const rtb_scene_shard *shard, void *prims, size_t prim_chunk_bytes, void *box_lo, void *box_hi,
                         size_t box_chunk_bytes, void *tex_or_null, size_t tex_chunk_bytes);
+int rtb_shard_allgather_bytes(const rtb_scene_shard *shard, void *base, size_t chunk_bytes);
+int rtb_shard_max_int(const rtb_scene_shard *shard, int *d_value); /* in place: max over the ranks */
 int rtb_scene_create_sharded(const void *objects, size_t n_objects, int kind, int device, unsigned flags,
                              const rtb_scene_shard *shard, rtb_scene **out);
 

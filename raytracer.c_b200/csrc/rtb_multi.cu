@@ -248,6 +248,19 @@ int rtb_shard_allgather(const rtb_scene_shard *shard, void *prims, size_t prim_c
   return RTB_OK;
 }
 
+int rtb_shard_allgather_bytes(const rtb_scene_shard *shard, void *base, size_t chunk_bytes)
+{
+  ncclComm_t comm = static_cast<ncclComm_t>(shard->nccl);
+  RTB_NCCL(nccl_api().AllGather(static_cast<char *>(base) + (size_t)shard->rank * chunk_bytes, base, chunk_bytes, ncclChar, comm, 0));
+  return RTB_OK;
+}
+
+int rtb_shard_max_int(const rtb_scene_shard *shard, int *d_value)
+{
+  RTB_NCCL(nccl_api().AllReduce(d_value, d_value, 1, ncclInt32, ncclMax, static_cast<ncclComm_t>(shard->nccl), 0));
+  return RTB_OK;
+}
+
 static void shard_samples(int begin, int end, int rank, int n_ranks, int &s0, int &s1)
 {
   const long long spp = (long long)end - begin;

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128, 8) k_render_sm(const __grid_constant__ Re
       {
         PrimView p = load_prim(big_phase ? A.sv.big : A.sv.prims, prim_i);
         test_prim_filtered<true>(p, big_phase ? ~prim_i : prim_i, st.o, st.d, rf.ofx, rf.ofy, rf.ofz, rf.dfx, rf.dfy,
-                           rf.dfz, rf.o_abs1, best, ts.prim_tests);
+                           rf.dfz, rf.o_abs1, best, ts.prim_tests, big_phase ? nullptr : A.sv.tri64);
         prim_i++;
         if (prim_i == prim_end)
         {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128, 8) k_render_pw(const __grid_constant__ Re
         int first = code >> 3, count = (code & 7) + 1;
         for (int k = 0; k < count; k++)
         {
-          test_prim(load_prim(A.sv.prims, first + k), first + k, st.o, st.d, best);
+          test_prim(load_prim(A.sv.prims, first + k), first + k, st.o, st.d, best, A.sv.tri64);
           if (STATS) ts.prim_tests++;
         }
         rayf_update_tmax(rf, best);

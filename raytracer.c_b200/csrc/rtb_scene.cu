@@ -92,9 +92,13 @@ __global__ void k_marshal_spheres(const SphereIn *__restrict__ in, int n, PrimRe
   }
 }
 
+/* tri64 (9 doubles per triangle) keeps the positions exactly as given; *inexact is raised when a position
+ * is not float-representable -- only then does the scene keep tri64 for the exact test (the reference's
+ * arithmetic is all-double, vector.h:7; OBJ-loaded meshes are float, tinyobj_loader.h:470-481) */
 __global__ void k_marshal_tris(const RefVertex *__restrict__ verts, int n_tris, int obj, int gid_first,
                                PrimRec *__restrict__ out, float4 *__restrict__ box_lo,
-                               float4 *__restrict__ box_hi, float2 *__restrict__ tex)
+                               float4 *__restrict__ box_hi, float2 *__restrict__ tex, double *__restrict__ tri64,
+                               int *__restrict__ inexact)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tris)
@@ -102,24 +106,34 @@ __global__ void k_marshal_tris(const RefVertex *__restrict__ verts, int n_tris, 
   const double *p = reinterpret_cast<const double *>(verts + 3 * (size_t)i);
   /* 3 vertices x 5 doubles, contiguous */
   float v[3][3], t[3][2];
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  bool exact = true;
 #pragma unroll
   for (int k = 0; k < 3; k++)
   {
-    v[k][0] = __double2float_rn(p[5 * k + 0]);
-    v[k][1] = __double2float_rn(p[5 * k + 1]);
-    v[k][2] = __double2float_rn(p[5 * k + 2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+      const double x = p[5 * k + a];
+      v[k][a] = __double2float_rn(x);
+      exact = exact && ((double)v[k][a] == x);
+      lo[a] = fminf(lo[a], __double2float_rd(x)); /* the box contains the double triangle */
+      hi[a] = fmaxf(hi[a], __double2float_ru(x));
+      if (tri64)
+        tri64[9 * (size_t)i + 3 * k + a] = x;
+    }
     t[k][0] = __double2float_rn(p[5 * k + 3]);
     t[k][1] = __double2float_rn(p[5 * k + 4]);
   }
+  if (!exact && inexact)
+    *inexact = 1; /* benign race: every writer stores the same value */
   PrimRec r;
   r.a = make_float4(v[0][0], v[0][1], v[0][2], v[1][0]);
   r.b = make_float4(v[1][1], v[1][2], v[2][0], v[2][1]);
   r.c = make_float4(v[2][2], __int_as_float(gid_first + i), __uint_as_float((unsigned)obj), 0.0f);
   out[i] = r;
-  box_lo[i] = make_float4(fminf(v[0][0], fminf(v[1][0], v[2][0])), fminf(v[0][1], fminf(v[1][1], v[2][1])),
-                          fminf(v[0][2], fminf(v[1][2], v[2][2])), 0.0f);
-  box_hi[i] = make_float4(fmaxf(v[0][0], fmaxf(v[1][0], v[2][0])), fmaxf(v[0][1], fmaxf(v[1][1], v[2][1])),
-                          fmaxf(v[0][2], fmaxf(v[1][2], v[2][2])), 0.0f);
+  box_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+  box_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.0f);
   if (tex)
   {
     tex[3 * (size_t)i + 0] = make_float2(t[0][0], t[0][1]);
@@ -587,6 +601,16 @@ __global__ void k_reorder(const unsigned *__restrict__ vals, int n, const PrimRe
   }
 }
 
+__global__ void k_reorder64(const unsigned *__restrict__ vals, int n, const double *__restrict__ in, double *__restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const unsigned p = vals ? vals[i] : (unsigned)i;
+  for (int k = 0; k < 9; k++)
+    out[9 * (size_t)i + k] = in[9 * (size_t)p + k];
+}
+
 /* ---- host side ------------------------------------------------------------------- */
 
 namespace
@@ -731,7 +755,7 @@ int gather_scene_objects(const RefSceneObject *objs, size_t n, HostScene &hs)
 }
 
 /* pick the oversized spheres (see file header): radius > 32 x the median primitive size,
- * at most 16 of them, largest first */
+ * at most 32 of them, largest first */
 std::vector<char> choose_big(const HostScene &hs)
 {
   std::vector<char> big(hs.spheres.size(), 0);
@@ -772,7 +796,9 @@ std::vector<char> choose_big(const HostScene &hs)
   std::sort(cand.begin(), cand.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &b) {
     return a.first > b.first || (a.first == b.first && a.second < b.second);
   });
-  for (size_t k = 0; k < cand.size() && k < 16; k++)
+  /* at most 32: big_list_select_test keeps its candidates in a 32-bit mask.  Further oversized spheres
+   * stay in the tree: correct, only slower (tests/test_gpu_parity.py::test_many_oversized_spheres) */
+  for (size_t k = 0; k < cand.size() && k < 32; k++)
     big[cand[k].second] = 1;
   return big;
 }
@@ -868,6 +894,9 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   DevBuf<PrimRec> d_unsorted;
   DevBuf<float4> d_lo, d_hi, d_node_lo, d_node_hi;
   DevBuf<float2> d_tex_unsorted;
+  DevBuf<double> d_tri64_unsorted; /* triangle vertices as given; kept only if some are not float-representable */
+  DevBuf<int> d_inexact;
+  int h_inexact = 0;
   DevBuf<RefVertex> d_stage;
   DevBuf<unsigned> d_bounds, d_vals, d_vals_sorted;
   DevBuf<BuildParams> d_bp;
@@ -898,6 +927,12 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
     RTB_CUDA(d_unsorted.alloc(N_alloc));
     RTB_CUDA(d_lo.alloc(N_alloc));
     RTB_CUDA(d_hi.alloc(N_alloc));
+    if (n_tris)
+    {
+      RTB_CUDA(d_tri64_unsorted.alloc(9 * N_alloc));
+      RTB_CUDA(d_inexact.alloc(1));
+      RTB_CUDA(cudaMemsetAsync(d_inexact.p, 0, sizeof(int), 0));
+    }
     if (want_tex)
     {
       RTB_CUDA(d_tex_unsorted.alloc(3 * N_alloc));
@@ -940,7 +975,8 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
           RTB_CUDA(cudaMemcpyAsync(d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, cudaMemcpyHostToDevice, 0));
           k_marshal_tris<<<(int)((cnt + T - 1) / T), T>>>(d_stage.p, (int)cnt, m.obj, (int)(m.gid_first + (long long)t0),
                                                           d_unsorted.p + offset, d_lo.p + offset, d_hi.p + offset,
-                                                          want_tex ? d_tex_unsorted.p + 3 * offset : nullptr);
+                                                          want_tex ? d_tex_unsorted.p + 3 * offset : nullptr,
+                                                          d_tri64_unsorted.p + 9 * offset, d_inexact.p);
           RTB_CUDA(cudaGetLastError());
         }
         tri_first += m.n_tris;
@@ -952,7 +988,20 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
                                       sizeof(float2) * 3 * tri_chunk);
         if (grc != RTB_OK)
           return grc;
+        /* double-precision vertices travel only if some rank found a coordinate that needs them */
+        grc = rtb_shard_max_int(shard, d_inexact.p);
+        if (grc != RTB_OK)
+          return grc;
+        RTB_CUDA(cudaMemcpy(&h_inexact, d_inexact.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (h_inexact)
+        {
+          grc = rtb_shard_allgather_bytes(shard, d_tri64_unsorted.p + 9 * n_bs, sizeof(double) * 9 * tri_chunk);
+          if (grc != RTB_OK)
+            return grc;
+        }
       }
+      else if (n_tris)
+        RTB_CUDA(cudaMemcpyAsync(&h_inexact, d_inexact.p, sizeof(int), cudaMemcpyDeviceToHost, 0));
     }
 
     /* scene box -> guard box, padding, Morton grid (all on the device) */
@@ -1070,6 +1119,17 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   float ms = 0;
   RTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
 
+  if (N > 0 && h_inexact)
+  {
+    /* some mesh coordinate is not float-representable (a mesh transformed in double, main.c:140-147): keep the
+     * caller's doubles, in BVH order, for the exact triangle test and the surface normal */
+    RTB_CUDA(scene_alloc(sc.get(), &sc->d_tri64, 9 * (N + 1)));
+    RTB_CUDA(cudaMemsetAsync(sc->d_tri64 + 9 * N, 0, sizeof(double) * 9, 0)); /* the degenerate triangle of empty slots */
+    k_reorder64<<<(int)((N + 255) / 256), 256>>>(d_vals_sorted.p, (int)N, d_tri64_unsorted.p, sc->d_tri64);
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaStreamSynchronize(0));
+    dev_bytes += sizeof(double) * 9 * N;
+  }
   if (N > 0)
   {
     if (!h_bp.finite)
@@ -1108,6 +1168,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   view.mats = sc->d_mats;
   view.colors = sc->d_colors;
   view.tex = sc->d_tex;
+  view.tri64 = sc->d_tri64;
 
   sc->info.n_objects = hs.n_objects;
   sc->info.n_spheres = hs.spheres.size();
@@ -1119,6 +1180,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   sc->info.build_ms = ms;
   sc->info.bvh_depth = bvh_depth;
   sc->info.device = device;
+  sc->info.double_triangles = h_inexact ? 1 : 0;
   *out = sc.release();
   return RTB_OK;
 }

@@ -261,7 +261,9 @@ __device__ __forceinline__ uint4 wf_ld(const uint4 *p, bool stream)
   return stream ? __ldcs(p) : *p;
 }
 
-template <bool STATS, int V>
+/* T64: the scene carries double-precision triangle vertices (SceneView::tri64); a separate instantiation so
+ * that the common case -- float-representable meshes -- has no extra branch in the leaf loop */
+template <bool STATS, int V, bool T64 = false>
 __global__ void __launch_bounds__(128, WfTraceCfg<V>::blocks)
 k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
            unsigned long long *totals, int refill_idle, int node_exit, const unsigned *__restrict__ perm)
@@ -392,7 +394,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
         const int code = ~cur;
         const int first = code >> 3, count = (code & 7) + 1;
         for (int k = 0; k < count; k++)
-          test_prim(load_prim(sv.prims, first + k), first + k, o, d, best);
+          test_prim(load_prim(sv.prims, first + k), first + k, o, d, best, T64 ? sv.tri64 : nullptr);
         prim_tests += (unsigned)count;
         rayf_update_tmax(rf, best);
         cur = POP2 ? stack.pop2(rf) : stack.pop(rf);
@@ -422,7 +424,14 @@ static void launch_trace(bool stats, int sm_count, cudaStream_t stream, const Sc
                          int refill_idle, int node_exit, const unsigned *perm)
 {
   const int blocks = sm_count * WfTraceCfg<V>::blocks;
-  if (stats)
+  if (sv.tri64 != nullptr)
+  {
+    if (stats)
+      k_wf_trace<true, V, true><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
+    else
+      k_wf_trace<false, V, true><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
+  }
+  else if (stats)
     k_wf_trace<true, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
   else
     k_wf_trace<false, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
@@ -653,8 +662,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       switch (variant)
       {
       case 2: launch_trace<2>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 4: launch_trace<4>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 18: launch_trace<18>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 22: launch_trace<22>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 54: launch_trace<54>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 86: launch_trace<86>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
@@ -662,7 +669,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       case 182: launch_trace<182>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 214: launch_trace<214>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 10: launch_trace<10>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 14: launch_trace<14>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       case 6: launch_trace<6>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       default: launch_trace<0>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
       }

@@ -27,6 +27,8 @@ def scene(name):
     api = ol.pkg.api
     if name == "c1":
         return api.scene_default(96, 54), 96, 54
+    if name == "c1_320":  # the reference's default frame (main.c:24-30): 320x180
+        return api.scene_default(320, 180), 320, 180
     return api.scene_sphere_field(60, 64, 36, mix=(0.3, 0.4, 0.2)), 64, 36
 
 
@@ -39,14 +41,26 @@ def one(job):
     return name, seed, mean, ctr[0]
 
 
+SCENES = (("c1", "c1_converged_96x54.npz", S), ("dielectric", "dielectric_converged_64x36.npz", S // 2),
+          ("c1_320", "c1_converged_320x180.npz", S))
+
+
 def main():
+    """python tests/golden/make_converged.py [scene ...] [--procs N]   (default: every scene, all cores)"""
+    args = sys.argv[1:]
+    procs = os.cpu_count() or 1
+    if "--procs" in args:
+        k = args.index("--procs")
+        procs = int(args[k + 1])
+        del args[k:k + 2]
+    todo = [sc for sc in SCENES if not args or sc[0] in args]
     jobs = []
-    for name, spp in (("c1", S), ("dielectric", S // 2)):
+    for name, _, spp in todo:
         for k in range(N_FULL + N_FULL // 4):
             jobs.append((name, SEED0 + 7919 * k, spp))
-    with mp.Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+    with mp.Pool(min(len(jobs), procs)) as pool:
         res = pool.map(one, jobs, chunksize=1)
-    for name, fname, spp in (("c1", "c1_converged_96x54.npz", S), ("dielectric", "dielectric_converged_64x36.npz", S // 2)):
+    for name, fname, spp in todo:
         rs = [r for r in res if r[0] == name]
         full, quarter = rs[:N_FULL], rs[N_FULL:]
         mean = np.mean([r[2] for r in full], axis=0)

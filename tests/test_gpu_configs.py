@@ -1,0 +1,140 @@
+"""Parity on the SHAPES of the named configs (BASELINE.json configs / SURVEY.md 8d), at frames the CPU
+oracle finishes in seconds: the full scene of each config (all 10 000 spheres, depth 64, ...) with a
+reduced frame and sample count.  GPU through the C ABI vs oracle/oracle.c with the same Philox streams:
+per-pixel float sums to 1e-3 relative, ray_count exactly.  Plus the PSNR gate at the reference's own default
+frame, 320x180 (main.c:24-30), against a converged render of the UNMODIFIED reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import psnr_u8
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _compare(gpu_api, ol, source, W, H, spp, depth, rtol=1e-3, atol=1e-4, sample_begin=0):
+    cam = gpu_api.init_camera(W, H)
+    desc = gpu_api.make_desc(W, H, sample_begin, sample_begin + spp, max_depth=depth)
+    with gpu_api.Scene(source) as sc:
+        fb, acc, ctr = sc.render(cam, desc, want_accum=True)
+    want, (rays, _) = ol.render_sum(source, cam, W, H, spp, rng="philox", dielectric="stochastic", max_depth=depth,
+                                    sample_offset=sample_begin)
+    assert ctr.rays == rays, "ray_count (trace_path invocations, raytracer.c:484) must match the oracle exactly"
+    assert ctr.paths == W * H * spp
+    np.testing.assert_allclose(acc, want, rtol=rtol, atol=atol)
+    want_fb = ol.tonemap(want, spp)
+    assert np.abs(fb.astype(int) - want_fb.astype(int)).max() <= 1
+    return ctr
+
+
+def test_c2_shape_10k_spheres_depth_8(gpu_api, ol):
+    """C2: 10 000 random spheres, mixed materials, max depth 8 -- the whole integrator, not only nearest hits"""
+    objs = gpu_api.scene_sphere_field(10000, 1920, 1080)
+    assert len(objs) >= 10000
+    ctr = _compare(gpu_api, ol, objs, 160, 90, 1, 8, sample_begin=5)
+    assert 2.0 < ctr.rays / ctr.paths < 10.0
+
+
+def test_c4_shape_dielectric_metal_heavy(gpu_api, ol):
+    """C4: the 10 000-sphere field with 40 % dielectric / 40 % mirror at the 4K aspect, depth 8"""
+    objs = gpu_api.scene_sphere_field(10000, 3840, 2160, mix=(0.2, 0.4, 0.4))
+    _compare(gpu_api, ol, objs, 128, 72, 1, 8, rtol=2e-3, atol=2e-4)
+
+
+def test_c5_shape_all_dielectric_depth_64(gpu_api, ol):
+    """C5: deep-bounce stress -- 2 000 spheres, 90 % dielectric, max depth 64: bounce words up to 0x140,
+    130 kernel launches per wave, paths that survive all 65 levels"""
+    objs = gpu_api.scene_sphere_field(2000, 512, 512, mix=(0.1, 0.9, 0.0))
+    ctr = _compare(gpu_api, ol, objs, 96, 96, 2, 64, rtol=2e-3, atol=2e-4)
+    assert ctr.rays / ctr.paths > 6.0, "the stress scene must actually go deep"
+
+
+def test_c5_depth_boundaries(gpu_api, ol):
+    """depths around the encoding limits: 63/64/65 on a mirror + dielectric field (no early roulette exits)"""
+    objs = gpu_api.scene_sphere_field(300, 256, 256, mix=(0.0, 0.5, 0.5))
+    for depth in (63, 65, 128):
+        _compare(gpu_api, ol, objs, 32, 32, 1, depth, rtol=3e-3, atol=3e-4)
+
+
+def test_c3_shape_mesh_room_depth_5(gpu_api, ol):
+    """C3: the height-field mesh room (here 2 x 64 x 64 triangles) + its spheres, depth 5, two samples"""
+    W, H = 96, 54
+    verts = gpu_api.heightfield_mesh(64, 20 * W / H * 0.98)
+    holder = gpu_api.mesh_room(verts, W, H)
+    _compare(gpu_api, ol, holder, W, H, 2, 5)
+
+
+def test_psnr_c1_at_the_reference_default_frame(gpu_api, ol):
+    """C1 at 320x180 (main.c:24-30) against 32 768 spp of the unmodified reference (8 srand() seeds x 4 096
+    spp, tests/golden/make_converged.py).  Gate: >= 40 dB, or the reference's own noise floor + 1 dB
+    (an independent 8 192-spp reference render against the 32 768-spp one)."""
+    path = os.path.join(GOLD, "c1_converged_320x180.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/c1_converged_320x180.npz not generated")
+    W, H, gpu_spp = 320, 180, 131072
+    g = np.load(path)
+    ref_full, ref_quarter = g["mean"].astype(np.float64), g["mean_quarter"].astype(np.float64)
+    objs = gpu_api.scene_default(W, H)
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        _, acc, ctr = sc.render(cam, gpu_api.make_desc(W, H, 0, gpu_spp, max_depth=5), want_accum=True)
+    gpu_mean = acc.astype(np.float64) / gpu_spp
+    fb_ref, fb_q, fb_gpu = ol.tonemap(ref_full, 1), ol.tonemap(ref_quarter, 1), ol.tonemap(gpu_mean, 1)
+    floor, got = psnr_u8(fb_q, fb_ref), psnr_u8(fb_gpu, fb_ref)
+    bias = (gpu_mean.mean() - ref_full.mean()) / ref_full.mean()
+    print(f"C1 320x180: PSNR(gpu {gpu_spp} spp, ref {int(g['spp'][0])} spp) = {got:.2f} dB; reference noise floor = {floor:.2f} dB; "
+          f"mean bias {bias:+.4f}; {ctr.rays / ctr.gpu_ms / 1e3:.0f} Mrays/s")
+    assert got >= min(40.0, floor + 1.0), (got, floor)
+    assert abs(bias) < 0.01
+
+
+# ---- meshes whose vertices are genuine doubles (apply_matrix, main.c:140-147) --------------------------
+
+def _transformed_mesh(gpu_api, grid, W, H):
+    """a height-field mesh rotated, scaled and shifted in double: its coordinates are no longer floats"""
+    verts = gpu_api.heightfield_mesh(grid, 20 * W / H * 0.5)
+    a, b = 0.3, -0.2
+    ry = np.array([[np.cos(a), 0, np.sin(a), 0], [0, 1, 0, 0], [-np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]])
+    rx = np.array([[1, 0, 0, 0], [0, np.cos(b), -np.sin(b), 0], [0, np.sin(b), np.cos(b), 0], [0, 0, 0, 1]])
+    m = ry @ rx @ np.diag([0.7, 1.3, 0.9, 1.0])
+    m[:3, 3] = [0.123456789, 1.0 / 3.0, -2.0 / 7.0]
+    gpu_api.apply_matrix(verts, m)
+    assert not np.array_equal(verts["pos"], verts["pos"].astype(np.float32).astype(np.float64))
+    return verts
+
+
+def test_double_vertices_nearest_hit_is_bit_exact(gpu_api, ol):
+    """the caller's double vertices reach the exact triangle test unrounded: ids, t, points and normals equal
+    the oracle's brute-force loop over the SAME doubles, bit for bit (round 1 narrowed them to float silently)"""
+    W, H = 96, 54
+    verts = _transformed_mesh(gpu_api, 48, W, H)
+    holder = gpu_api.mesh_room(verts, W, H)
+    rng = np.random.default_rng(23)
+    rays = random_rays_in_room_local(rng, 6000)
+    want = ol.intersect_rays(holder, rays)
+    with gpu_api.Scene(holder, all_trees=True) as sc:
+        assert sc.info.double_triangles == 1
+        for mode in (1, 3, 4, 5, 0):
+            got = sc.trace_rays(rays, use_bvh=mode)
+            assert np.array_equal(got["ids"], want["ids"]), mode
+            hit = want["ids"] >= 0
+            assert np.array_equal(got["points"][hit], want["points"][hit]), mode
+            assert np.array_equal(got["normals"][hit], want["normals"][hit]), mode
+    # a float-representable mesh keeps the compact float records
+    with gpu_api.Scene(gpu_api.mesh_room(gpu_api.heightfield_mesh(8, 10.0), W, H)) as sc:
+        assert sc.info.double_triangles == 0
+
+
+def test_double_vertices_render_matches_oracle(gpu_api, ol):
+    W, H = 64, 36
+    verts = _transformed_mesh(gpu_api, 32, W, H)
+    holder = gpu_api.mesh_room(verts, W, H)
+    _compare(gpu_api, ol, holder, W, H, 2, 5)
+
+
+def random_rays_in_room_local(rng, n):
+    from conftest import random_rays_in_room
+    return random_rays_in_room(rng, n)

@@ -372,3 +372,24 @@ def test_tree_walks_on_adversarial_rays(gpu_api):
             for k in ("ids", "prims", "t", "points", "normals"):
                 assert np.array_equal(got[k], brute[k]), (mode, k)
     assert (brute["ids"] >= 0).mean() > 0.9
+
+
+def test_many_oversized_spheres(gpu_api):
+    """more oversized spheres than the every-ray list holds (32): the rest go into the tree, whose Morton
+    grid they stretch -- slower, but the nearest hit must still be the brute-force one, ties included"""
+    rng = np.random.default_rng(17)
+    W, H = 64, 36
+    small = gpu_api.scene_sphere_field(500, W, H)
+    room = small[:6].copy()                       # the six r = 10 000 walls
+    extra = np.repeat(room, 7, axis=0)            # 42 more oversized spheres, slightly displaced
+    extra["center"] += rng.uniform(-3.0, 3.0, size=extra["center"].shape)
+    extra["radius"] *= rng.uniform(0.999, 1.001, size=len(extra))
+    objs = np.concatenate([small, extra])
+    rays = random_rays_in_room(rng, 4000)
+    with gpu_api.Scene(objs) as sc:
+        assert sc.info.n_big_prims == 32
+        bvh, brute = sc.trace_rays(rays, use_bvh=1), sc.trace_rays(rays, use_bvh=0)
+        cam = gpu_api.init_camera(W, H)
+        _, acc, ctr = sc.render(cam, gpu_api.make_desc(W, H, 0, 2), want_accum=True)
+    _assert_hits_equal(bvh, brute, "48 oversized spheres")
+    assert np.isfinite(acc).all() and ctr.rays > 0
