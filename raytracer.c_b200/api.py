@@ -255,12 +255,13 @@ def render(objects, camera, width, height, samples):
 
 # ---- the C ABI ----------------------------------------------------------------------------
 
-def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0, integrator=0, profile=1):
+def make_desc(width, height, sample_begin, sample_end, max_depth=5, seed=abi.SCENE_SEED, kernel=0, tune=0, planes=0, tune2=0, integrator=0, profile=1,
+              dielectric=0):
     d = abi.RtbRenderDesc()
     d.width, d.height = width, height
     d.sample_begin, d.sample_end = sample_begin, sample_end
     d.max_depth = max_depth
-    d.dielectric_mode = 0
+    d.dielectric_mode = dielectric  # 0 stochastic (one child per dielectric vertex), 1 the reference's two-way split
     d.seed = seed
     d.kernel = kernel
     d.reserved = tune

@@ -27,6 +27,7 @@ struct PathState
   float tr, tg, tb; /* throughput */
   int depth;
   bool alive;
+  unsigned branch; /* 1 on the camera ray; a dielectric vertex of the SPLIT estimator gives its children 2b and 2b+1 */
 };
 
 struct PathCounters
@@ -50,14 +51,21 @@ __device__ __forceinline__ void path_begin(const RenderArgs &A, PathState &st, i
   st.tr = st.tg = st.tb = 1.0f;
   st.depth = 0;
   st.alive = true;
+  st.branch = 1u;
 }
 
 /* One vertex of the path: the body of trace_path after the scene query.
- * `sum` accumulates throughput * (emission | background). */
+ * `sum` accumulates throughput * (emission | background).
+ * SPLIT: the reference's own dielectric estimator (raytracer.c:522-529): BOTH children are traced, the
+ * retro-"refraction" ray with weight kt and the reflection with weight kr.  `st` continues as the first
+ * (refraction, evaluated first upstream), `*second` as the other; second->alive says whether it exists. */
+template <bool SPLIT = false>
 __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, const HitRec &best, unsigned pixel,
                                            unsigned sample, float &sr, float &sg, float &sb, PathCounters &pc,
-                                           Surface *surf_out)
+                                           Surface *surf_out, PathState *second = nullptr)
 {
+  if (SPLIT)
+    second->alive = false;
   if (best.t >= 1e300)
   {
     sr += st.tr * RT_BACKGROUND; sg += st.tg * RT_BACKGROUND; sb += st.tb * RT_BACKGROUND;
@@ -81,7 +89,7 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
   sr += st.tr * m1.x; sg += st.tg * m1.y; sb += st.tb * m1.z;
 
   /* Russian roulette, one draw per vertex (raytracer.c:497-502) */
-  const unsigned bounce_word = (unsigned)st.depth | 0x100u;
+  const unsigned bounce_word = (unsigned)st.depth | (st.branch << 8);
   uint4 w = philox4x32_10(make_uint4(pixel, sample, bounce_word, 0u), A.key);
   if ((w.x >> 1) >= __float_as_uint(m0.w))
   {
@@ -111,7 +119,20 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
     double kt = __dmul_rn(__dsub_rn(1.0, fresnel), 1.0);
     double p = kr < 0.05 ? 0.05 : (kr > 0.95 ? 0.95 : kr);
     float wgt;
-    if (uniform31(w.y) < p)
+    if (SPLIT)
+    {
+      const d3 dir_in = st.d;
+      *second = st;
+      second->d = d3_normalize(reflect_dir(d3_scale(dir_in, 1.0), s.normal));
+      const float wr = (float)kr;
+      second->tr *= wr; second->tg *= wr; second->tb *= wr;
+      second->branch = (st.branch << 1) | 1u;
+      second->alive = true;
+      st.d = d3_normalize(d3_scale(dir_in, -1.0));
+      st.branch = st.branch << 1;
+      wgt = (float)kt;
+    }
+    else if (uniform31(w.y) < p)
     {
       st.d = d3_normalize(reflect_dir(d3_scale(st.d, 1.0), s.normal));
       wgt = (float)__ddiv_rn(kr, p);
@@ -157,12 +178,23 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
   }
   st.o = s.point;
   st.depth++;
+  if (SPLIT && second->alive)
+  {
+    second->o = s.point;
+    second->depth = st.depth;
+  }
   if (st.depth > A.max_depth)
   {
     /* the next trace_path call returns BACKGROUND without intersecting (raytracer.c:487) */
     pc.rays++;
     sr += st.tr * RT_BACKGROUND; sg += st.tg * RT_BACKGROUND; sb += st.tb * RT_BACKGROUND;
     st.alive = false;
+    if (SPLIT && second->alive)
+    {
+      pc.rays++;
+      sr += second->tr * RT_BACKGROUND; sg += second->tg * RT_BACKGROUND; sb += second->tb * RT_BACKGROUND;
+      second->alive = false;
+    }
   }
 }
 

@@ -605,9 +605,16 @@ static int check_desc(const rtb_render_desc *d)
     rtb_set_error("rtb_render_desc.integrator: RTB_INTEGRATOR_PATH or RTB_INTEGRATOR_WHITTED");
     return RTB_EINVAL;
   }
-  if (d->dielectric_mode != RTB_DIELECTRIC_STOCHASTIC)
+  if (d->dielectric_mode != RTB_DIELECTRIC_STOCHASTIC && d->dielectric_mode != RTB_DIELECTRIC_SPLIT)
   {
-    rtb_set_error("dielectric_mode: only RTB_DIELECTRIC_STOCHASTIC runs on the GPU");
+    rtb_set_error("dielectric_mode: RTB_DIELECTRIC_STOCHASTIC or RTB_DIELECTRIC_SPLIT");
+    return RTB_EINVAL;
+  }
+  if (d->dielectric_mode == RTB_DIELECTRIC_SPLIT &&
+      (d->max_depth > 16 || (d->kernel != 0 && d->kernel != 6) || d->integrator != RTB_INTEGRATOR_PATH))
+  {
+    /* 2^(depth+1) rays per path: the reference's estimator is tractable for shallow paths only (its MAX_DEPTH is 5) */
+    rtb_set_error("RTB_DIELECTRIC_SPLIT: wavefront path tracer only (kernel 0 or 6), max_depth <= 16");
     return RTB_EINVAL;
   }
   return RTB_OK;
@@ -688,6 +695,8 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     }
     else
       want_threads = std::min<long long>(64ll << 20, path_cap[dev].load());
+    if (desc->dielectric_mode == RTB_DIELECTRIC_SPLIT) /* the queues hold up to 64 entries per path slot */
+      want_threads >>= std::min(desc->max_depth + 1, 6);
     want_threads = std::max<long long>(want_threads, (long long)n_px);
   }
   int splits = (int)std::min<long long>(std::max<long long>(1, (want_threads + (long long)n_px - 1) / (long long)n_px), 64);

@@ -48,6 +48,8 @@ struct WfQueue
   double2 *d_yz;  /* direction.y, direction.z */
   uint4 *path;    /* path slot id, throughput r, g, b (float bits) */
   uint4 *hit;     /* best.t (two words), gid, slot */
+  unsigned *branch; /* SPLIT dielectric estimator only (else NULL): branch id of the ray (PathState::branch) */
+  unsigned cap;     /* entries the arrays hold; only the SPLIT estimator can run into it */
 };
 
 
@@ -132,7 +134,8 @@ __device__ __forceinline__ unsigned ray_sort_key(const SceneView &sv, const d3 &
 /* warp-aggregated append: every lane of the warp must call this */
 __device__ __forceinline__ void wf_enqueue(const WfQueue &q, unsigned *count, bool want, int lane, const d3 &o, const d3 &d,
                                            unsigned pid, float tr, float tg, float tb, const HitRec &seed,
-                                           unsigned *keys = nullptr, unsigned key = 0u)
+                                           unsigned *keys = nullptr, unsigned key = 0u, unsigned branch = 1u,
+                                           unsigned *overflow = nullptr)
 {
   const unsigned m = __ballot_sync(WF_FULL, want);
   if (m == 0u)
@@ -145,6 +148,13 @@ __device__ __forceinline__ void wf_enqueue(const WfQueue &q, unsigned *count, bo
   if (want)
   {
     const unsigned i = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+    if (overflow != nullptr && i >= q.cap)
+    {
+      *overflow = 1u; /* the split tree outgrew the queue: the host retries with fewer paths per wave */
+      return;
+    }
+    if (q.branch)
+      __stcs(q.branch + i, branch);
     /* queue traffic is streamed once: evict-first, so it does not push the BVH out of L2 */
     __stcs(q.o_xy + i, make_double2(o.x, o.y));
     __stcs(q.oz_dx + i, make_double2(o.z, d.x));
@@ -217,6 +227,8 @@ __global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ 
     __stcs(q.d_yz + i, make_double2(st.d.y, st.d.z));
     __stcs(q.path + i, make_uint4(pid, __float_as_uint(st.tr), __float_as_uint(st.tg), __float_as_uint(st.tb)));
     __stcs(q.hit + i, pack_hit(seed));
+    if (q.branch)
+      __stcs(q.branch + i, 1u);
   }
   for (int off = 16; off > 0; off >>= 1)
     exact += __shfl_xor_sync(WF_FULL, exact, off);
@@ -274,7 +286,7 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
   constexpr int SD = WfTraceCfg<V>::sd;
   __shared__ int2 s_stack[SD > 0 ? SD : 1][128];
   const int lane = threadIdx.x & 31;
-  const unsigned n = *n_ptr;
+  const unsigned n = min(*n_ptr, q.cap);
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   /* batch: large enough to make the atomic rare, small enough that every warp gets work */
   unsigned batch = (n / (n_warps * 4u)) & ~31u;
@@ -440,12 +452,17 @@ static void launch_trace(bool stats, int sm_count, cudaStream_t stream, const Sc
 /* ---- shading of a whole queue ------------------------------------------------------------------
  * Thread i handles ray i: the body of trace_path after intersect() (path_shade), then, if the
  * path goes on, the oversized-list test of the NEXT ray and a warp-aggregated append. */
+/* SPLIT: the reference's deterministic two-way split at dielectrics (raytracer.c:522-529): a vertex may append
+ * two rays, several rays of one path slot are in flight at once (so the accumulator is updated with atomics
+ * and the sums are no longer bit-reproducible), and the queue can overflow (flag -> host retries smaller). */
+template <bool SPLIT>
 __global__ void __launch_bounds__(128, WF_SHADE_BLOCKS) k_wf_shade(const __grid_constant__ RenderArgs A, int wave, int depth, WfQueue qin,
                                                   const unsigned *__restrict__ n_in, WfQueue qout, unsigned *n_out,
-                                                  float4 *__restrict__ planes, unsigned *keys_out, int sort_mode)
+                                                  float4 *__restrict__ planes, unsigned *keys_out, int sort_mode,
+                                                  unsigned *overflow)
 {
   const int lane = threadIdx.x & 31;
-  const unsigned n = *n_in;
+  const unsigned n = min(*n_in, qin.cap);
   const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   const unsigned n_px = (unsigned)(A.width * A.height);
@@ -461,9 +478,13 @@ __global__ void __launch_bounds__(128, WF_SHADE_BLOCKS) k_wf_shade(const __grid_
     st.tr = st.tg = st.tb = 0.0f;
     st.depth = depth;
     st.alive = false;
+    st.branch = 1u;
+    PathState second;
+    second.alive = false;
     unsigned pid = 0;
-    HitRec seed;
+    HitRec seed, seed2;
     seed.t = DBL_MAX; seed.gid = 0x7FFFFFFF; seed.slot = 0;
+    seed2 = seed;
     if (i < n)
     {
       const uint4 p = __ldcs(qin.path + i);
@@ -477,19 +498,37 @@ __global__ void __launch_bounds__(128, WF_SHADE_BLOCKS) k_wf_shade(const __grid_
       const unsigned plane = pid / n_px;
       const unsigned pixel = pid - plane * n_px;
       const unsigned sample = (unsigned)(A.s_begin + (int)plane * A.chunk + wave);
-      float4 acc = __ldcs(planes + pid);
-      const float4 before = acc;
       pc.rays++;
       pc.rays_hit++;
-      path_shade(A, st, best, pixel, sample, acc.x, acc.y, acc.z, pc, nullptr);
-      if (__float_as_uint(acc.x) != __float_as_uint(before.x) || __float_as_uint(acc.y) != __float_as_uint(before.y) ||
-          __float_as_uint(acc.z) != __float_as_uint(before.z))
-        __stcs(planes + pid, acc);
+      if (SPLIT)
+      {
+        st.branch = __ldcs(qin.branch + i);
+        float r = 0.0f, g = 0.0f, b2 = 0.0f;
+        path_shade<true>(A, st, best, pixel, sample, r, g, b2, pc, nullptr, &second);
+        float *acc = reinterpret_cast<float *>(planes + pid);
+        if (r != 0.0f) atomicAdd(acc + 0, r);
+        if (g != 0.0f) atomicAdd(acc + 1, g);
+        if (b2 != 0.0f) atomicAdd(acc + 2, b2);
+        if (second.alive)
+          ray_seed_hit(A.sv, second.o, second.d, seed2, exact);
+      }
+      else
+      {
+        float4 acc = __ldcs(planes + pid);
+        const float4 before = acc;
+        path_shade<false>(A, st, best, pixel, sample, acc.x, acc.y, acc.z, pc, nullptr);
+        if (__float_as_uint(acc.x) != __float_as_uint(before.x) || __float_as_uint(acc.y) != __float_as_uint(before.y) ||
+            __float_as_uint(acc.z) != __float_as_uint(before.z))
+          __stcs(planes + pid, acc);
+      }
       if (st.alive)
         ray_seed_hit(A.sv, st.o, st.d, seed, exact);
     }
     wf_enqueue(qout, n_out, st.alive, lane, st.o, st.d, pid, st.tr, st.tg, st.tb, seed, keys_out,
-               (keys_out && st.alive) ? ray_sort_key(A.sv, st.o, st.d, sort_mode) : 0u);
+               (keys_out && st.alive) ? ray_sort_key(A.sv, st.o, st.d, sort_mode) : 0u, st.branch, SPLIT ? overflow : nullptr);
+    if (SPLIT)
+      wf_enqueue(qout, n_out, second.alive, lane, second.o, second.d, pid, second.tr, second.tg, second.tb, seed2, nullptr, 0u,
+                 second.branch, overflow);
   }
   wf_add_counters(A.counters, lane, pc.rays, pc.rays_hit, exact, 0ull, 0ull);
 }
@@ -533,6 +572,17 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     return RTB_EINVAL;
   }
   const int n_bounces = A.max_depth + 1;
+  /* SPLIT dielectric estimator: a path becomes a tree of up to 2^(depth+1) rays; the queues hold `split_factor`
+   * entries per path slot (exact worst case up to max_depth 5, the reference's MAX_DEPTH; beyond that the
+   * overflow flag reports a scene that needs more) */
+  const bool split = A.dielectric_mode == RTB_DIELECTRIC_SPLIT;
+  const size_t split_factor = split ? ((size_t)1 << std::min(A.max_depth + 1, 6)) : 1;
+  const size_t cap = slots * split_factor;
+  if (cap >= (1ull << 31))
+  {
+    rtb_set_error("wavefront: width*height*planes*split factor must stay below 2^31");
+    return RTB_EINVAL;
+  }
 
   /* tuning word (desc->reserved): bits 0-7 refill threshold, 8-15 node-phase exit threshold,
    * 16-23 trace kernel variant; desc->reserved2: ray sorting mode (0 = off) */
@@ -549,14 +599,15 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     node_exit = 0; /* pure while-while */
   if ((variant & (8 | 16)) != 0 && A.sv.nodes4q == nullptr && A.sv.root_ref >= 0 && A.sv.root_ref != RTB_REF_NONE)
     variant = 6; /* the scene has no BVH4 (tree too deep for its stack): BVH2 walk */
-  const int sort_mode = desc->reserved2 & 0xFF;
+  const int sort_mode = split ? 0 : (desc->reserved2 & 0xFF);
   const int sort_from = 1;                                           /* primary rays are coherent already */
   const int sort_until = (desc->reserved2 >> 8) & 0xFF ? (desc->reserved2 >> 8) & 0xFF : 255;
 
   /* one allocation: 2 queues x 5 arrays of 16 B, the planes, sort buffers, the per-wave counters */
-  const size_t arr = align_up(slots * 16, 256);
-  const size_t arr4 = align_up(slots * 4, 256);
-  const size_t ctr_bytes = align_up(sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), 256);
+  const size_t arr = align_up(cap * 16, 256);
+  const size_t arr_planes = align_up(slots * 16, 256);
+  const size_t arr4 = align_up(cap * 4, 256);
+  const size_t ctr_bytes = align_up(sizeof(unsigned) * (2 * (size_t)(n_bounces + 2) + 1), 256);
   size_t sort_tmp_bytes = 0;
   if (sort_mode)
   {
@@ -564,7 +615,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, nul, nul, nul, nul, (int)slots, 0, 24, stream);
     sort_tmp_bytes = align_up(sort_tmp_bytes, 256);
   }
-  const size_t need = arr * 11 + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0);
+  const size_t need = arr * 10 + arr_planes + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0) + (split ? arr4 * 2 : 0);
   if (scene->wf_bytes < need)
   {
     if (scene->d_wf)
@@ -601,11 +652,20 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     q[k].d_yz = reinterpret_cast<double2 *>(p); p += arr;
     q[k].path = reinterpret_cast<uint4 *>(p); p += arr;
     q[k].hit = reinterpret_cast<uint4 *>(p); p += arr;
+    q[k].branch = nullptr;
+    q[k].cap = (unsigned)cap;
   }
-  float4 *planes = reinterpret_cast<float4 *>(p); p += arr;
+  float4 *planes = reinterpret_cast<float4 *>(p); p += arr_planes;
   unsigned *counts = reinterpret_cast<unsigned *>(p);            /* [n_bounces + 2] queue lengths */
   unsigned *fetch = counts + (n_bounces + 2);                    /* [n_bounces + 2] trace fetch cursors */
+  unsigned *overflow = fetch + (n_bounces + 2);                  /* SPLIT: a queue ran out of entries */
   p += ctr_bytes;
+  if (split)
+  {
+    q[0].branch = reinterpret_cast<unsigned *>(p); p += arr4;
+    q[1].branch = reinterpret_cast<unsigned *>(p); p += arr4;
+    RTB_CUDA(cudaMemsetAsync(overflow, 0, sizeof(unsigned), stream));
+  }
   unsigned *keys = nullptr, *keys_sorted = nullptr, *iota = nullptr, *perm = nullptr;
   void *sort_tmp = nullptr;
   if (sort_mode)
@@ -675,8 +735,11 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       mark();
       if (sort_out) /* slots beyond the queue's end keep the largest key and sort to the back */
         RTB_CUDA(cudaMemsetAsync(keys, 0xFF, slots * 4, stream));
-      k_wf_shade<<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes,
-                                                   sort_out ? keys : nullptr, sort_mode);
+      if (split)
+        k_wf_shade<true><<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes, nullptr, 0, overflow);
+      else
+        k_wf_shade<false><<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes,
+                                                            sort_out ? keys : nullptr, sort_mode, nullptr);
       launches += 2;
       if (sort_out)
       {
@@ -690,6 +753,18 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   k_wf_sum_planes<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(planes, A.splits, (unsigned)n_px, d_accum);
   RTB_CUDA(cudaGetLastError());
   launches++;
+  if (split)
+  {
+    unsigned h_overflow = 0;
+    RTB_CUDA(cudaMemcpyAsync(&h_overflow, overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    RTB_CUDA(cudaStreamSynchronize(stream));
+    if (h_overflow)
+    {
+      rtb_set_error("RTB_DIELECTRIC_SPLIT: the split tree of some path outgrew the ray queue (max_depth > 5 with many "
+                    "dielectric surfaces); use RTB_DIELECTRIC_STOCHASTIC, the same estimator in expectation");
+      return RTB_EINVAL;
+    }
+  }
   if (phase_ms)
   {
     /* ev = [t0 trace t1] shade/generate [t2 trace t3] ...: odd gaps are trace launches */

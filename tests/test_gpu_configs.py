@@ -138,3 +138,85 @@ def test_double_vertices_render_matches_oracle(gpu_api, ol):
 def random_rays_in_room_local(rng, n):
     from conftest import random_rays_in_room
     return random_rays_in_room(rng, n)
+
+
+# ---- the reference's own dielectric estimator: deterministic two-way split (raytracer.c:522-529) --------
+
+@pytest.mark.parametrize("scene,depth", [("c1", 5), ("dielectric", 5), ("dielectric", 3), ("mesh", 4)])
+def test_dielectric_split_matches_oracle(gpu_api, ol, scene, depth):
+    """RTB_DIELECTRIC_SPLIT traces BOTH children at a dielectric vertex like upstream; against the oracle in the
+    same mode (which is bit-identical to the reference under libc rand()): ray_count exact -- it now counts the
+    whole split tree -- and sums to 1e-3"""
+    W, H, SPP = 64, 36, 3
+    if scene == "c1":
+        src = gpu_api.scene_default(W, H)
+    elif scene == "dielectric":
+        src = gpu_api.scene_sphere_field(200, W, H, mix=(0.1, 0.6, 0.2))
+    else:
+        src = gpu_api.mesh_room(gpu_api.heightfield_mesh(24, 20 * W / H * 0.98), W, H)
+    cam = gpu_api.init_camera(W, H)
+    desc = gpu_api.make_desc(W, H, 1, 1 + SPP, max_depth=depth, dielectric=1)
+    with gpu_api.Scene(src) as sc:
+        fb, acc, ctr = sc.render(cam, desc, want_accum=True)
+        _, acc_st, ctr_st = sc.render(cam, gpu_api.make_desc(W, H, 1, 1 + SPP, max_depth=depth), want_accum=True)
+    want, (rays, _) = ol.render_sum(src, cam, W, H, SPP, rng="philox", dielectric="split", max_depth=depth, sample_offset=1)
+    assert ctr.rays == rays
+    np.testing.assert_allclose(acc, want, rtol=1e-3, atol=1e-4)
+    # the sphere field and the mesh room (its glass ball) hold M_REFRACTION surfaces, the default scene may not
+    has_dielectric = scene in ("dielectric", "mesh") or bool((np.asarray(src["flags"]) & 8).any())
+    if has_dielectric:
+        assert ctr.rays > ctr_st.rays, "the split traces more rays than the one-child estimator"
+    else:
+        assert ctr.rays == ctr_st.rays  # no dielectric surface: same paths; sums equal up to the order of additions
+        np.testing.assert_allclose(acc, acc_st, rtol=1e-5, atol=1e-6)
+
+
+def test_dielectric_split_reports_overflow_instead_of_dropping_rays(gpu_api):
+    """2^(depth+1) rays per path: beyond max_depth 5 an all-dielectric scene can outgrow the queue; that is an
+    error, never a silently darker image"""
+    W, H = 32, 18
+    objs = gpu_api.scene_sphere_field(300, W, H, mix=(0.0, 1.0, 0.0))
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        with pytest.raises(gpu_api.RtbError, match="SPLIT"):
+            sc.render(cam, gpu_api.make_desc(W, H, 0, 1, max_depth=16, dielectric=1))
+        with pytest.raises(gpu_api.RtbError, match="SPLIT"):
+            sc.render(cam, gpu_api.make_desc(W, H, 0, 1, max_depth=17, dielectric=1))  # rejected up front
+        fb, _, ctr = sc.render(cam, gpu_api.make_desc(W, H, 0, 1, max_depth=5, dielectric=1))  # exact worst case fits
+        assert ctr.rays > 0
+
+
+def test_drop_in_render_honours_dielectric_mode_and_total_samples(gpu_api):
+    """RenderParams.dielectric_mode and .total_samples used to be ignored by render_ex()"""
+    import ctypes as C
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    _, host = pkg.load()
+    W, H, SPP = 64, 36, 4
+    objs = gpu_api.scene_default(W, H)
+    cam = gpu_api.init_camera(W, H)
+    opt = pkg.abi.Options()
+    opt.width, opt.height, opt.samples = W, H, SPP
+
+    def run(**kw):
+        rp = pkg.abi.RenderParams()
+        host.render_params_default(C.byref(rp))
+        rp.num_gpus = 1
+        for k, v in kw.items():
+            setattr(rp, k, v)
+        fb = np.zeros((H, W, 3), np.uint8)
+        acc = np.zeros((H, W, 3), np.float32)
+        rp.accum_out = acc.ctypes.data_as(C.POINTER(C.c_float))
+        before = C.c_longlong.in_dll(host, "ray_count").value
+        host.render_ex(fb.ctypes.data, objs.ctypes.data, len(objs), C.byref(cam), C.byref(opt), C.byref(rp))
+        return fb, acc, C.c_longlong.in_dll(host, "ray_count").value - before
+
+    fb_s, acc_s, rays_s = run()
+    fb_d, acc_d, rays_d = run(dielectric_mode=1)
+    assert rays_d >= rays_s  # equal when the scene has no dielectric surface
+    # a caller that renders its share of a larger job: mean over total_samples, not over its own count
+    fb_half, acc_half, _ = run(total_samples=2 * SPP)
+    assert np.array_equal(acc_half, acc_s)
+    want = np.minimum(1.0, (acc_s.astype(np.float64) / (2 * SPP)) ** 0.2) * 255.0
+    assert np.abs(fb_half.astype(int) - np.floor(want).astype(int)).max() <= 1
+    assert fb_half.astype(int).sum() < fb_s.astype(int).sum()
