@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ 
  * 32 / 64 = with 16: 6 / 12 of the 24 plane-byte conversions of a node on the ALU + FMA pipes instead of
  * the conversion pipe; 128 = pops read the top two stack entries at once.
  * (Measured and removed in round 2, profiles/r2_wf_tuning.md: prefetching the next rays of the batch into
- * L1 / L2 after every refill; reading the FP32 walk set-up from the queue, written by the producer.) */
+ * L1 / L2 after every refill; reading the FP32 walk set-up from the queue, written by the producer;
+ * prefetching a leaf's primitives when the walk reaches it; dropping the whole stack at once when a hit
+ * ends before the nearest entry ever pushed.) */
 template <int V> struct WfTraceCfg { static constexpr int blocks = (V & 1) ? 10 : 8; static constexpr int sd = (V & 4) ? 0 : WF_SMEM_STACK; };
 
 __device__ __forceinline__ double2 wf_ld(const double2 *p, bool stream)
