@@ -403,7 +403,7 @@ def main_gpu(args):
             else:
                 host.render_ex(fb_host.ctypes.data, src.ctypes.data, len(src), C.byref(cam), C.byref(opt), C.byref(rp))
         else:
-            comm.render_host(src, cam, desc, want_counters=False)  # rtb_render_multi, collective
+            comm.render_host(src, cam, desc, want_counters=False, fb=fb_host)  # rtb_render_multi, collective
 
     def time_e2e(src):
         e2e_step(src)  # warm

@@ -474,12 +474,14 @@ class Comm:
                "rtb_comm_scene_create")
         return MultiScene(self, handles, keep)
 
-    def render_host(self, source, camera, desc, want_accum=False, want_counters=True):
+    def render_host(self, source, camera, desc, want_accum=False, want_counters=True, fb=None):
         """collective: the whole render() with host buffers on all GPUs (rtb_render_multi).
-        The framebuffer (and sums) are valid on the process that holds rank 0."""
+        The framebuffer (and sums) are valid on the process that holds rank 0.  `fb`: the caller's own
+        (H, W, 3) uint8 buffer, like the framebuffer main.c allocates once (main.c:413)."""
         ptr, n, kind, keep = _source_records(source)
         cam = camera.as_array()
-        fb = np.zeros((desc.height, desc.width, 3), dtype=np.uint8)
+        if fb is None:
+            fb = np.zeros((desc.height, desc.width, 3), dtype=np.uint8)
         acc = np.zeros((desc.height, desc.width, 3), dtype=np.float32) if want_accum else None
         ctr = abi.RtbCounters() if want_counters else None
         _check(self._cu.rtb_render_multi(self._h, ptr, n, kind, cam.ctypes.data_as(C.POINTER(C.c_double)), C.byref(desc),

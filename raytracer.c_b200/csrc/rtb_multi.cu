@@ -26,6 +26,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -377,10 +379,15 @@ static int rank_render_host(RankCtx &R, int n_ranks, const void *objects, size_t
                             float *accum_or_null, rtb_counters *counters)
 {
   rtb_scene *scene = nullptr;
+  const bool timing = getenv("RTB_TIMING") != nullptr; /* development aid: where an end-to-end call spends its time */
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   int rc = rank_scene_create(R, n_ranks, objects, n_objects, kind, 0u, &scene);
   if (rc != RTB_OK)
     return rc;
+  const double t1 = now();
   rc = rank_render_reduce(R, n_ranks, scene, camera12, desc, nullptr, counters);
+  const double t2 = now();
   if (rc == RTB_OK)
   {
     const size_t elems = (size_t)3 * desc->width * desc->height;
@@ -399,7 +406,11 @@ static int rank_render_host(RankCtx &R, int n_ranks, const void *objects, size_t
       rc = RTB_ECUDA;
     }
   }
+  const double t3 = now();
   rtb_scene_destroy(scene);
+  if (timing)
+    fprintf(stderr, "rtb_render_multi rank %d: scene %.2f ms, launch %.2f ms, wait + read-back %.2f ms, destroy %.2f ms\n", R.rank,
+            t1 - t0, t2 - t1, t3 - t2, now() - t3);
   return rc;
 }
 

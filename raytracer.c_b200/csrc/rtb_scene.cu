@@ -28,6 +28,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 /* ---- error text ------------------------------------------------------------- */
@@ -654,6 +655,93 @@ static cudaError_t pool_setup(int device)
   return e;
 }
 
+/* ---- host -> device upload of a caller's pageable array ------------------------------------------
+ * The reference's driver malloc()s its scene (main.c:413), so the 120 MB of Vertex records of C3 arrive in
+ * pageable memory: one cudaMemcpy of it runs at the speed of the driver's single staging thread (~10 GB/s,
+ * 12 ms), a quarter of the PCIe link.  Here a few host threads copy interleaved 4 MB chunks into their own
+ * page-locked double buffers and DMA them from there, each on its own stream.  The streams are ordinary
+ * (blocking) streams: work on the legacy default stream -- the marshalling kernel -- orders itself after them. */
+namespace
+{
+const size_t kStageChunk = 4u << 20;
+const int kStageMaxThreads = 8;
+struct StageLane
+{
+  char *pinned[2] = { nullptr, nullptr };
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done[2] = { nullptr, nullptr };
+};
+struct StagePool
+{
+  std::mutex mutex; /* one upload at a time per device */
+  StageLane lanes[kStageMaxThreads];
+  int ready = 0;
+};
+StagePool g_stage[64];
+
+cudaError_t stage_lane_init(StageLane &l)
+{
+  for (int k = 0; k < 2; k++)
+  {
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&l.pinned[k]), kStageChunk, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&l.done[k], cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaStreamCreate(&l.stream);
+}
+
+cudaError_t upload_pageable(int device, void *dst, const void *src, size_t bytes, int threads)
+{
+  cudaPointerAttributes attr;
+  const bool host_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError(); /* an unregistered pointer is not an error */
+  threads = std::max(1, std::min(threads, kStageMaxThreads));
+  if (host_pinned || bytes < 2 * kStageChunk || threads < 2 || device < 0 || device >= 64)
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, 0);
+  StagePool &pool = g_stage[device];
+  std::lock_guard<std::mutex> lock(pool.mutex);
+  for (; pool.ready < threads; pool.ready++)
+  {
+    cudaError_t e = stage_lane_init(pool.lanes[pool.ready]);
+    if (e != cudaSuccess)
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, 0); /* no page-locked memory left: plain copy */
+  }
+  const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+  std::vector<cudaError_t> err((size_t)threads, cudaSuccess);
+  std::vector<std::thread> workers;
+  for (int t = 0; t < threads; t++)
+    workers.emplace_back([&, t]() {
+      cudaError_t e = cudaSetDevice(device);
+      StageLane &l = pool.lanes[t];
+      int turn = 0;
+      for (size_t c = (size_t)t; c < n_chunks && e == cudaSuccess; c += (size_t)threads, turn++)
+      {
+        const int slot = turn & 1;
+        if (turn >= 2)
+          e = cudaEventSynchronize(l.done[slot]); /* the DMA that last read this buffer */
+        const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+        memcpy(l.pinned[slot], static_cast<const char *>(src) + off, len);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(static_cast<char *>(dst) + off, l.pinned[slot], len, cudaMemcpyHostToDevice, l.stream);
+        if (e == cudaSuccess)
+          e = cudaEventRecord(l.done[slot], l.stream);
+      }
+      /* the buffers may be refilled by the next upload only after their DMAs: wait here, the copies of the
+       * other lanes keep the link busy meanwhile */
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(l.stream);
+      err[(size_t)t] = e;
+    });
+  for (std::thread &w : workers)
+    w.join();
+  for (cudaError_t e : err)
+    if (e != cudaSuccess)
+      return e;
+  return cudaSuccess;
+}
+} // namespace
+
 template <typename T>
 struct DevBuf
 {
@@ -950,6 +1038,10 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
       /* raw Vertex arrays go up as they are (120 B per triangle) and are converted on the
        * device; staging is bounded so huge meshes do not double their footprint */
       const size_t chunk_tris = 1u << 21;
+      /* host threads staging the pageable vertex array (see upload_pageable); ranks of one box share the host */
+      int upload_threads = sharded ? 2 : 6;
+      if (const char *e = getenv("RTB_UPLOAD_THREADS"))
+        upload_threads = atoi(e);
       /* this rank's share of the concatenated triangle list: everything, or chunk `rank` of G */
       const size_t my_first = sharded ? std::min(n_tris, tri_chunk * (size_t)shard->rank) : 0;
       const size_t my_end = sharded ? std::min(n_tris, my_first + tri_chunk) : n_tris;
@@ -972,7 +1064,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
           const size_t cnt = std::min(chunk_tris, hi - g0);
           const size_t t0 = g0 - tri_first;    /* first triangle of the piece inside its mesh */
           const size_t offset = n_bs + g0;     /* its slot in the (unsorted) primitive arrays */
-          RTB_CUDA(cudaMemcpyAsync(d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, cudaMemcpyHostToDevice, 0));
+          RTB_CUDA(upload_pageable(device, d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, upload_threads));
           k_marshal_tris<<<(int)((cnt + T - 1) / T), T>>>(d_stage.p, (int)cnt, m.obj, (int)(m.gid_first + (long long)t0),
                                                           d_unsorted.p + offset, d_lo.p + offset, d_hi.p + offset,
                                                           want_tex ? d_tex_unsorted.p + 3 * offset : nullptr,

@@ -10,6 +10,10 @@
  *   -g <device>              CUDA device ordinal
  *   -c default|spheres:N|mesh:GRID|obj:FILE
  *   -i path|whitted          integrator: trace_path (upstream default) or cast_ray (raytracer.c:207-211)
+ *   -G <gpus>                render on GPUs 0..n-1 of the box (samples sharded, one ncclReduce; default $RTB_NUM_GPUS or 1)
+ *   -D stochastic|split      dielectric estimator: one child per vertex (default) or the reference's two-way split
+ *   -m <sx,sy,sz,ry,tx,ty,tz> with obj:FILE -- place the mesh like the reference's driver would: scale, rotation about
+ *                            y (degrees), translation, composed into a mat4 and applied with apply_matrix (main.c:140-147)
  * Deliberately NOT reproduced: the option parser's mis-parse of values whose second
  * character is h/w/s/o and the SIGINT handler's double free.
  */
@@ -24,16 +28,16 @@ int rt_write_png(const char *filename, int w, int h, int comp, const void *data,
 typedef struct
 {
   Options options;
-  int max_depth, device, integrator;
+  int max_depth, device, integrator, gpus, dielectric;
   uint64_t seed;
-  const char *scene;
+  const char *scene, *placement;
 } Cli;
 
 static void usage(const char *prog)
 {
   fprintf(stderr, "Usage: %s -w <width> -h <height> -s <samples per pixel> -o <filename>\n", prog);
   fprintf(stderr, "       [-d <max depth>] [-S <seed>] [-g <cuda device>] [-c default|spheres:N|mesh:GRID|obj:FILE]\n");
-  fprintf(stderr, "       [-i path|whitted]\n");
+  fprintf(stderr, "       [-i path|whitted] [-G <gpus>] [-D stochastic|split] [-m sx,sy,sz,ry_deg,tx,ty,tz]\n");
 }
 
 static bool parse_cli(int argc, char **argv, Cli *cli)
@@ -63,6 +67,9 @@ static bool parse_cli(int argc, char **argv, Cli *cli)
     case 'g': cli->device = atoi(val); break;
     case 'c': cli->scene = val; break;
     case 'i': cli->integrator = (strcmp(val, "whitted") == 0) ? RT_INTEGRATOR_WHITTED : RT_INTEGRATOR_PATH; break;
+    case 'G': cli->gpus = atoi(val); break;
+    case 'D': cli->dielectric = (strcmp(val, "split") == 0) ? RT_DIELECTRIC_SPLIT : RT_DIELECTRIC_STOCHASTIC; break;
+    case 'm': cli->placement = val; break;
     default:
       fprintf(stderr, "unknown option '%s'\n", a);
       return false;
@@ -109,6 +116,9 @@ int main(int argc, char **argv)
   rp.seed = cli.seed;
   rp.device = cli.device;
   rp.integrator = cli.integrator;
+  rp.dielectric_mode = cli.dielectric;
+  if (cli.gpus > 0)
+    rp.num_gpus = cli.gpus;
 
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -137,6 +147,18 @@ int main(int argc, char **argv)
     }
     else if (!load_obj(cli.scene + 4, &mesh))
       return EXIT_FAILURE;
+    if (cli.placement)
+    {
+      /* scale, then rotate about y, then translate: M = T * Ry * S, row-major like vector.h */
+      double v[7] = { 1, 1, 1, 0, 0, 0, 0 };
+      sscanf(cli.placement, "%lf,%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
+      const double a = v[3] * (PI / 180), c = cos(a), s = sin(a);
+      mat4 m = { c * v[0], 0, s * v[2], v[4],
+                 0, v[1], 0, v[5],
+                 -s * v[0], 0, c * v[2], v[6],
+                 0, 0, 0, 1 };
+      apply_matrix(&mesh, m);
+    }
     SceneObject *scene = NULL;
     Sphere *spheres = NULL;
     size_t n = scene_mesh_room(&scene, &spheres, &mesh, opt->width, opt->height);
