@@ -451,6 +451,278 @@ static void launch_trace(bool stats, int sm_count, cudaStream_t stream, const Sc
     k_wf_trace<false, V><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, refill_idle, node_exit, perm);
 }
 
+
+/* ---- nearest hit for a whole queue, "ray pool" form --------------------------------------------------
+ * k_wf_trace ties a ray to a lane: whatever phase most lanes are in runs, the others idle -- 16.9 of 32
+ * lanes per issued instruction (profiles/r2_wf_trace_ncu.md: node step 20 lanes, leaf tests 8-12, refill
+ * 12-16, pop loops 4-7).  Here a warp owns a POOL of WF_POOL_RAYS rays whose walk state lives in shared
+ * memory and whose traversal stacks live in global memory, indexed by pool slot, so ANY lane can advance
+ * ANY ray.  Three lists (slots waiting for a node step, for a leaf test, free slots) are kept by
+ * warp-aggregated appends; every turn the warp takes up to 32 slots from ONE list and runs that phase with
+ * (nearly) all lanes.  Same node step, same exact tests, same acceptance rule: the hit records are
+ * bit-identical to k_wf_trace's. */
+#ifndef WF_POOL_RAYS
+#define WF_POOL_RAYS 64
+#endif
+
+/* The WalkStack interface for a pool slot.  Entry k of the slot's stack lives in global memory at
+ * base[k * WF_POOL_RAYS] (L1 does not allocate on a store, so a pop of it is an L2 round trip); the TOP entry
+ * is therefore kept in shared memory (loaded into top_ref / top_dist for the duration of a step): the pop
+ * that follows a node without hit children -- the common one -- never leaves the SM.  Deeper pops read four
+ * entries at once. */
+struct PoolStack
+{
+  int2 *base;
+  int sp;         /* entries in global memory (the cached top not counted) */
+  int top_ref;    /* RTB_REF_NONE: no cached top */
+  float top_dist;
+  __device__ __forceinline__ void push(int2 e)
+  {
+    if (top_ref != RTB_REF_NONE)
+    {
+      base[(size_t)sp * WF_POOL_RAYS] = make_int2(top_ref, __float_as_int(top_dist));
+      sp++;
+    }
+    top_ref = e.x;
+    top_dist = __int_as_float(e.y);
+  }
+  __device__ __forceinline__ int pop(const RayF &rf)
+  {
+    if (top_ref != RTB_REF_NONE)
+    {
+      const int r = top_ref;
+      top_ref = RTB_REF_NONE;
+      if (top_dist <= rf.tmax)
+        return r;
+    }
+    while (sp > 0)
+    {
+      int2 e[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        e[k] = base[(size_t)max(sp - 1 - k, 0) * WF_POOL_RAYS];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (sp - 1 - k >= 0 && __int_as_float(e[k].y) <= rf.tmax)
+        {
+          sp = sp - 1 - k;
+          return e[k].x;
+        }
+      sp = max(sp - 4, 0);
+    }
+    return RTB_REF_NONE;
+  }
+};
+
+struct PoolShared /* one per warp */
+{
+  int cur[WF_POOL_RAYS], sp[WF_POOL_RAYS];
+  float idx[WF_POOL_RAYS], idy[WF_POOL_RAYS], idz[WF_POOL_RAYS];
+  float oodx[WF_POOL_RAYS], oody[WF_POOL_RAYS], oodz[WF_POOL_RAYS];
+  float tmax[WF_POOL_RAYS], tbase[WF_POOL_RAYS];
+  int t_lo[WF_POOL_RAYS], t_hi[WF_POOL_RAYS], gid[WF_POOL_RAYS], slot[WF_POOL_RAYS];
+  int top_ref[WF_POOL_RAYS];
+  float top_dist[WF_POOL_RAYS];
+  unsigned ray[WF_POOL_RAYS];
+  unsigned char node_list[WF_POOL_RAYS], leaf_list[WF_POOL_RAYS], free_list[WF_POOL_RAYS];
+};
+
+/* every lane of the warp calls this: lanes with `want` append `value` to list[0 .. n) */
+__device__ __forceinline__ void pool_append(unsigned char *list, int &n, bool want, unsigned value, int lane)
+{
+  const unsigned m = __ballot_sync(WF_FULL, want);
+  if (want)
+    list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned char)value;
+  n += __popc(m);
+}
+
+template <bool STATS, bool T64>
+__global__ void __launch_bounds__(128, 8)
+k_wf_trace_pool(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
+                unsigned long long *totals, int2 *__restrict__ stacks, int leaf_min)
+{
+  __shared__ PoolShared s_pool[4];
+  const int lane = threadIdx.x & 31;
+  PoolShared &P = s_pool[threadIdx.x >> 5];
+  const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int2 *const my_stacks = stacks + (size_t)gwarp * RTB_STACK_SIZE * WF_POOL_RAYS;
+  const unsigned n = min(*n_ptr, q.cap);
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned batch = (n / (n_warps * 4u)) & ~31u;
+  batch = batch < 32u ? 32u : (batch > 512u ? 512u : batch);
+  unsigned next = 0, end = 0; /* the warp's current batch */
+  bool pool_empty = n == 0u;
+
+  int n_node = 0, n_leaf = 0, n_free = WF_POOL_RAYS;
+  for (int k = lane; k < WF_POOL_RAYS; k += 32)
+    P.free_list[k] = (unsigned char)k;
+  __syncwarp();
+  unsigned node_visits = 0, prim_tests = 0;
+
+  while (true)
+  {
+    /* ---- which phase runs this turn: one that can fill the warp, else the fullest list ---- */
+    enum { PH_NODE, PH_LEAF, PH_FILL, PH_NONE };
+    const int can_fill = pool_empty ? 0 : n_free;
+    int phase;
+    if (can_fill >= 32) phase = PH_FILL;
+    else if (n_node >= 32) phase = PH_NODE;
+    else if (n_leaf >= leaf_min) phase = PH_LEAF;
+    else if (can_fill > 0 && can_fill >= n_node) phase = PH_FILL;
+    else if (n_node > 0) phase = PH_NODE;
+    else if (n_leaf > 0) phase = PH_LEAF;
+    else if (can_fill > 0) phase = PH_FILL;
+    else break;
+
+    int s = -1;                /* the pool slot this lane works on */
+    int nxt = RTB_REF_NONE;    /* where its ray stands afterwards */
+    bool worked = false;
+
+    if (phase == PH_FILL)
+    {
+      if (next >= end)
+      {
+        unsigned base = 0;
+        if (lane == 0)
+          base = atomicAdd(fetch_ctr, batch);
+        base = __shfl_sync(WF_FULL, base, 0);
+        if (base >= n)
+        {
+          pool_empty = true;
+          continue;
+        }
+        next = base;
+        end = min(base + batch, n);
+      }
+      const int k = min(min(32, n_free), (int)(end - next));
+      if (lane < k)
+      {
+        s = P.free_list[n_free - k + lane];
+        const unsigned ray = next + (unsigned)lane;
+        const double2 a = __ldcs(q.o_xy + ray), b = __ldcs(q.oz_dx + ray), c = __ldcs(q.d_yz + ray);
+        const d3 o = d3_make(a.x, a.y, b.x), d = d3_make(b.y, c.x, c.y);
+        const uint4 hv = __ldcs(q.hit + ray);
+        const HitRec best = unpack_hit(hv);
+        RayF rf;
+        rayf_basic(o, d, rf);
+        rf.idx = rf.idy = rf.idz = rf.oodx = rf.oody = rf.oodz = rf.tmax = rf.t_base = 0.0f;
+        worked = true;
+        if (rayf_walk_setup(sv, o, d, best, rf))
+        {
+          nxt = sv.root_ref;
+          P.sp[s] = 0;
+          P.top_ref[s] = RTB_REF_NONE;
+          P.idx[s] = rf.idx; P.idy[s] = rf.idy; P.idz[s] = rf.idz;
+          P.oodx[s] = rf.oodx; P.oody[s] = rf.oody; P.oodz[s] = rf.oodz;
+          P.tmax[s] = rf.tmax; P.tbase[s] = rf.t_base;
+          P.t_lo[s] = (int)hv.x; P.t_hi[s] = (int)hv.y; P.gid[s] = (int)hv.z; P.slot[s] = (int)hv.w;
+          P.ray[s] = ray;
+          P.cur[s] = nxt;
+        }
+        /* else: the seeded hit record in the queue is already final; the slot stays free */
+      }
+      n_free -= k;
+      next += (unsigned)k;
+    }
+    else if (phase == PH_NODE)
+    {
+      const int k = min(32, n_node);
+      if (lane < k)
+      {
+        s = P.node_list[n_node - k + lane];
+        RayF rf;
+        rf.idx = P.idx[s]; rf.idy = P.idy[s]; rf.idz = P.idz[s];
+        rf.oodx = P.oodx[s]; rf.oody = P.oody[s]; rf.oodz = P.oodz[s];
+        rf.tmax = P.tmax[s];
+        PoolStack stack = { my_stacks + s, P.sp[s], P.top_ref[s], P.top_dist[s] };
+        if (STATS) node_visits++;
+        nxt = node_step4q<0>(sv, rf, P.cur[s], stack);
+        if (nxt == RTB_REF_NONE)
+          nxt = stack.pop(rf);
+        P.sp[s] = stack.sp;
+        P.top_ref[s] = stack.top_ref;
+        P.top_dist[s] = stack.top_dist;
+        P.cur[s] = nxt;
+        worked = true;
+      }
+      n_node -= k;
+    }
+    else /* PH_LEAF */
+    {
+      const int k = min(32, n_leaf);
+      if (lane < k)
+      {
+        s = P.leaf_list[n_leaf - k + lane];
+        const unsigned ray = P.ray[s];
+        const double2 a = __ldcg(q.o_xy + ray), b = __ldcg(q.oz_dx + ray), c = __ldcg(q.d_yz + ray);
+        const d3 o = d3_make(a.x, a.y, b.x), d = d3_make(b.y, c.x, c.y);
+        HitRec best;
+        best.t = __hiloint2double(P.t_hi[s], P.t_lo[s]);
+        best.gid = P.gid[s];
+        best.slot = P.slot[s];
+        const int code = ~P.cur[s];
+        const int first = code >> 3, count = (code & 7) + 1;
+        const double t_before = best.t;
+        const int gid_before = best.gid;
+        for (int j = 0; j < count; j++)
+          test_prim(load_prim(sv.prims, first + j), first + j, o, d, best, T64 ? sv.tri64 : nullptr);
+        prim_tests += (unsigned)count;
+        RayF rf;
+        rf.tmax = P.tmax[s];
+        rf.t_base = P.tbase[s];
+        if (best.t != t_before || best.gid != gid_before)
+        {
+          rayf_update_tmax(rf, best);
+          P.tmax[s] = rf.tmax;
+          P.t_lo[s] = __double2loint(best.t); P.t_hi[s] = __double2hiint(best.t);
+          P.gid[s] = best.gid; P.slot[s] = best.slot;
+        }
+        PoolStack stack = { my_stacks + s, P.sp[s], P.top_ref[s], P.top_dist[s] };
+        nxt = stack.pop(rf);
+        P.sp[s] = stack.sp;
+        P.top_ref[s] = stack.top_ref;
+        P.cur[s] = nxt;
+        worked = true;
+      }
+      n_leaf -= k;
+    }
+
+    /* ---- where every worked-on ray goes next ---- */
+    const bool to_node = worked && nxt >= 0 && nxt != RTB_REF_NONE;
+    const bool to_leaf = worked && nxt < 0;
+    const bool finished = worked && nxt == RTB_REF_NONE;
+    if (finished && phase != PH_FILL)
+    {
+      /* the walk of this ray is over: its hit record goes back to the queue */
+      const HitRec best = { __hiloint2double(P.t_hi[s], P.t_lo[s]), P.gid[s], P.slot[s] };
+      __stcs(q.hit + P.ray[s], pack_hit(best));
+    }
+    __syncwarp();
+    pool_append(P.node_list, n_node, to_node, (unsigned)s, lane);
+    pool_append(P.leaf_list, n_leaf, to_leaf, (unsigned)s, lane);
+    pool_append(P.free_list, n_free, finished, (unsigned)s, lane);
+    __syncwarp();
+  }
+  wf_add_counters(totals, lane, 0ull, 0ull, prim_tests, STATS ? node_visits : 0u, 0ull);
+}
+
+static void launch_trace_pool(bool stats, int sm_count, cudaStream_t stream, const SceneView &sv, const WfQueue &q,
+                              const unsigned *n_ptr, unsigned *fetch, unsigned long long *totals, int2 *stacks, int leaf_min)
+{
+  const int blocks = sm_count * 8;
+  const bool t64 = sv.tri64 != nullptr;
+  if (stats)
+  {
+    if (t64) k_wf_trace_pool<true, true><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, stacks, leaf_min);
+    else k_wf_trace_pool<true, false><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, stacks, leaf_min);
+  }
+  else
+  {
+    if (t64) k_wf_trace_pool<false, true><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, stacks, leaf_min);
+    else k_wf_trace_pool<false, false><<<blocks, 128, 0, stream>>>(sv, q, n_ptr, fetch, totals, stacks, leaf_min);
+  }
+}
+
 /* ---- shading of a whole queue ------------------------------------------------------------------
  * Thread i handles ray i: the body of trace_path after intersect() (path_shade), then, if the
  * path goes on, the oversized-list test of the NEXT ray and a warp-aggregated append. */
@@ -617,7 +889,11 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, nul, nul, nul, nul, (int)slots, 0, 24, stream);
     sort_tmp_bytes = align_up(sort_tmp_bytes, 256);
   }
-  const size_t need = arr * 10 + arr_planes + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0) + (split ? arr4 * 2 : 0);
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device);
+  const bool pool = variant == 1024 && A.sv.nodes4q != nullptr; /* the ray-pool form of the trace kernel */
+  const size_t pool_bytes = pool ? align_up((size_t)sm_count * 8 * 4 * RTB_STACK_SIZE * WF_POOL_RAYS * sizeof(int2), 256) : 0;
+  const size_t need = arr * 10 + arr_planes + ctr_bytes + (sort_mode ? arr4 * 4 + sort_tmp_bytes : 0) + (split ? arr4 * 2 : 0) + pool_bytes;
   if (scene->wf_bytes < need)
   {
     if (scene->d_wf)
@@ -668,6 +944,12 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     q[1].branch = reinterpret_cast<unsigned *>(p); p += arr4;
     RTB_CUDA(cudaMemsetAsync(overflow, 0, sizeof(unsigned), stream));
   }
+  int2 *pool_stacks = nullptr;
+  if (pool)
+  {
+    pool_stacks = reinterpret_cast<int2 *>(p);
+    p += pool_bytes;
+  }
   unsigned *keys = nullptr, *keys_sorted = nullptr, *iota = nullptr, *perm = nullptr;
   void *sort_tmp = nullptr;
   if (sort_mode)
@@ -683,8 +965,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
 
   RTB_CUDA(cudaMemsetAsync(planes, 0, slots * 16, stream));
 
-  int sm_count = 148;
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device);
   const int shade_blocks = sm_count * 16;
   const long long gen_warps = (long long)A.n_tiles * A.splits;
   const int gen_blocks = (int)((gen_warps * 32 + 255) / 256);
@@ -721,6 +1001,10 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
       const bool sort_out = sort_mode && b + 1 >= sort_from && b + 1 <= sort_until && b + 1 < n_bounces;
       const unsigned *use_perm = sorted_in ? perm : nullptr;
       mark();
+      if (pool)
+        launch_trace_pool(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, pool_stacks,
+                          (desc->reserved & 0xFF00) ? std::min(std::max(node_exit, 1), 32) : 32);
+      else
       switch (variant)
       {
       case 2: launch_trace<2>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;

@@ -108,7 +108,7 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
         _, acc5, c5 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=wideq), want_accum=True)
         assert np.array_equal(acc5, base) and c5.rays == c0.rays
         # round 2: byte conversions split between the conversion and ALU/FMA pipes (32, 64), two-entry pops (128)
-        for v in (54, 86, 150, 182, 214):
+        for v in (54, 86, 150, 182, 214, 1024):
             _, accv, cv = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune=(v << 16) | (16 << 8)), want_accum=True)
             assert np.array_equal(accv, base) and cv.rays == c0.rays and cv.prim_tests == c5.prim_tests, v
         _, acc4, c4 = sc.render(cam, gpu_api.make_desc(W, H, 3, 3 + spp, max_depth=6, kernel=6, planes=planes, tune2=3), want_accum=True)
