@@ -150,14 +150,14 @@ def measured_peaks():
 
 
 def ncu_traffic(workload):
-    """dram bytes (read + write) summed over the k_wf_trace launches of ONE step, from the
-    committed ncu capture of the same command (profiles/ncu_traffic.json), if any"""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the AVERAGE k_wf_trace launch, from the
+    committed ncu launch list of the same command (profiles/ncu_traffic.json), if any"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
         if d.get("kernel") == "k_wf_trace":
-            return d.get(workload)
+            return d.get(workload + "_per_launch")
     return None
 
 
@@ -476,7 +476,8 @@ def main_gpu(args):
             l2_gbs = hit_rank * bytes_ray / sec / 1e9
             hbm_gbs = hit_rank * HBM_BYTES_RAY / sec / 1e9
             tflops = hit_rank * flops_ray / sec / 1e12
-            traffic = ncu_traffic(args.workload)
+            traffic_launch = ncu_traffic(args.workload)  # per launch
+            traffic = traffic_launch * trace_launches if traffic_launch else None  # per step
             per_launch = 1.0 / max(1, trace_launches)
             roofline = {
                 # what bounds the kernel is neither HBM nor the tensor cores (north_star: not a dense contraction):
@@ -484,7 +485,7 @@ def main_gpu(args):
                 "bound": "l2", "kernel": "k_wf_trace", "achieved": l2_gbs, "peak": l2_peak, "unit": "GB/s",
                 "frac": l2_gbs / l2_peak if l2_peak else None,
                 "peak_source": "measured in this run: rtb_probe_l2_bandwidth, 32 MB L2-resident buffer, ld.global.cg.v4 from all SMs",
-                "traffic": traffic * per_launch if traffic else None,
+                "traffic": traffic_launch,
                 "traffic_def": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from the committed ncu launch list of this command (profiles/ncu_traffic.json)",
                 "bytes_per_launch": hit_rank * bytes_ray * per_launch, "avg_launch_ms": trace_ms * per_launch,
                 "launches_per_step": trace_launches, "kernel_ms_per_step": trace_ms, "share_of_step": trace_share,
