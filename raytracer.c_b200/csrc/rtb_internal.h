@@ -75,6 +75,7 @@ struct Bvh4Node { float4 q[8]; };
 struct Bvh4QNode { float4 w[4]; };
 #define RTB_LEAF_MAX 4
 #define RTB_STACK_SIZE 64
+#define RTB_WF_MAX_GROUPS 4
 #define RTB_REF_NONE 0x7FFFFFFF
 
 struct SceneView
@@ -106,6 +107,8 @@ struct rtb_scene
   float *d_scratch = nullptr; /* split planes */
   size_t scratch_bytes = 0;
   void *d_wf = nullptr;       /* wavefront kernels: ray queues + accumulation planes (rtb_wavefront.cu) */
+  cudaStream_t wf_streams[RTB_WF_MAX_GROUPS] = {}; /* extra streams of the wavefront pipeline: one per plane group in flight ([0] unused: the caller's stream) */
+  cudaEvent_t wf_fork = nullptr, wf_joins[RTB_WF_MAX_GROUPS] = {};
   size_t wf_bytes = 0;
   unsigned long long *d_counters = nullptr;
   rtb_scene_info info{};

@@ -16,6 +16,7 @@ struct RenderArgs
   int s_begin, s_end, chunk, splits;
   int max_depth, dielectric_mode;
   int suspend_lanes; /* k_render_pw: suspend the walk when fewer lanes than this are walking */
+  int plane_base;    /* wavefront: first plane of the group this launch works on (two groups run on two streams) */
   uint2 key;
   float *out; /* [splits][height*width*3] */
   unsigned long long *counters;

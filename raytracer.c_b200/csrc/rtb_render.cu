@@ -639,6 +639,7 @@ static void fill_args(RenderArgs &A, const rtb_scene *scene, const double *camer
   A.max_depth = desc->max_depth;
   A.dielectric_mode = desc->dielectric_mode;
   A.suspend_lanes = (desc->reserved > 0 && desc->reserved <= 32) ? desc->reserved : RTB_SUSPEND_LANES;
+  A.plane_base = 0;
   A.key = make_uint2((unsigned)(desc->seed & 0xFFFFFFFFull), (unsigned)(desc->seed >> 32));
   A.counters = scene->d_counters;
 }
@@ -665,10 +666,10 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
    * separately and summed in order -- this fixes the floating-point summation order, so every
    * kernel variant gives the same bits for the same number of planes.
    * Megakernels: enough threads to fill 148 SMs a few times over even for small frames.
-   * Wavefront: up to 64 M paths in flight per wave (11.7 GB of queues out of 180 GB): the deep
-   * bounces then still have enough rays to fill 148 SMs and the per-launch tail of the
-   * persistent trace kernel is amortised (measured C3: 8 M 3.07, 33 M 3.48, 66 M 3.61 Grays/s);
-   * never more than a quarter of the free device memory. */
+   * Wavefront: up to 128 M paths in flight, in two plane groups of 64 M on two streams (23.4 GB of queues
+   * out of 180 GB): the deep bounces then still have enough rays to fill 148 SMs and the tail of one
+   * group's persistent kernel is covered by the other group's next kernel (measured C3, round 2: 32 M
+   * 4.19, 64 M 4.29, 128 M 4.35 Grays/s); never more than a quarter of the free device memory. */
   const bool wavefront = desc->kernel == 6 || desc->kernel == 0;
   if (!wavefront && desc->integrator == RTB_INTEGRATOR_PATH && scene->view.nodes == nullptr && scene->view.root_ref >= 0 &&
       scene->view.root_ref != RTB_REF_NONE)
@@ -682,6 +683,9 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     /* the free memory is read once per device (cudaMemGetInfo costs milliseconds, render() makes a
      * new scene per call); it also keeps the plane count -- and with it the summation order --
      * the same from call to call */
+    long long wave_paths = 128ll << 20; /* path slots in flight (both plane groups together): 23.4 GB of queues */
+    if (const char *e = getenv("RTB_WF_PATHS_M"))
+      wave_paths = std::max(1ll, atoll(e)) << 20;
     static std::atomic<long long> path_cap[64]; /* zero-initialised; scenes on several devices render from several host threads */
     const int dev = scene->device;
     if (dev < 0 || dev >= 64 || path_cap[dev].load() == 0)
@@ -691,10 +695,10 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
       const long long cap = std::max<long long>(1ll << 20, (long long)((free_b + scene->wf_bytes) / 4 / 192));
       if (dev >= 0 && dev < 64)
         path_cap[dev].store(cap);
-      want_threads = std::min<long long>(64ll << 20, cap);
+      want_threads = std::min<long long>(wave_paths, cap);
     }
     else
-      want_threads = std::min<long long>(64ll << 20, path_cap[dev].load());
+      want_threads = std::min<long long>(wave_paths, path_cap[dev].load());
     if (desc->dielectric_mode == RTB_DIELECTRIC_SPLIT) /* the queues hold up to 64 entries per path slot */
       want_threads >>= std::min(desc->max_depth + 1, 6);
     want_threads = std::max<long long>(want_threads, (long long)n_px);

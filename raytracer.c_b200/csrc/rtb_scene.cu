@@ -1463,6 +1463,11 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
     rtb_cache_park(scene->device, b.first, b.second);
   if (scene->d_wf)
     rtb_cache_park(scene->device, scene->d_wf, scene->wf_bytes);
+  for (int g = 0; g < RTB_WF_MAX_GROUPS; g++)
+  {
+    if (scene->wf_joins[g]) cudaEventDestroy(scene->wf_joins[g]);
+  }
+  if (scene->wf_fork) cudaEventDestroy(scene->wf_fork);
   if (scene->d_scratch)
     rtb_cache_park(scene->device, scene->d_scratch, scene->scratch_bytes);
   delete scene;

@@ -27,10 +27,12 @@
 #include "rtb_path.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include <cub/cub.cuh>
 
 #define WF_FULL 0xFFFFFFFFu
+#define WF_MAX_GROUPS RTB_WF_MAX_GROUPS /* plane groups in flight, one stream each */
 #ifndef WF_SMEM_STACK
 #define WF_SMEM_STACK 8
 #endif
@@ -204,10 +206,10 @@ __global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int tile = (int)(warp % A.n_tiles);
-  const int plane = (int)(warp / A.n_tiles);
+  const int plane = (int)(warp / A.n_tiles); /* within this launch's group of planes (A.plane_base is its first) */
   const int x = (tile % A.tiles_x) * 8 + (lane & 7);
   const int y = (tile / A.tiles_x) * 4 + (lane >> 3);
-  const int s = A.s_begin + plane * A.chunk + wave;
+  const int s = A.s_begin + (A.plane_base + plane) * A.chunk + wave;
   const bool valid = x < A.width && y < A.height && plane < n_valid_planes;
   const unsigned n_px = (unsigned)(A.width * A.height);
   const unsigned pixel = (unsigned)(y * A.width + x);
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(256, 4) k_wf_generate(const __grid_constant__ 
     HitRec seed;
     path_begin(A, st, x, y, pixel, (unsigned)s);
     ray_seed_hit(A.sv, st.o, st.d, seed, exact);
-    const unsigned pid = (unsigned)plane * n_px + pixel;
+    const unsigned pid = (unsigned)(A.plane_base + plane) * n_px + pixel;
     const unsigned i = (unsigned)plane * n_px + (tiled ? (unsigned)tile * 32u + (unsigned)lane : pixel);
     __stcs(q.o_xy + i, make_double2(st.o.x, st.o.y));
     __stcs(q.oz_dx + i, make_double2(st.o.z, st.d.x));
@@ -881,7 +883,8 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   const size_t arr = align_up(cap * 16, 256);
   const size_t arr_planes = align_up(slots * 16, 256);
   const size_t arr4 = align_up(cap * 4, 256);
-  const size_t ctr_bytes = align_up(sizeof(unsigned) * (2 * (size_t)(n_bounces + 2) + 1), 256);
+  const size_t ctr_one = align_up(sizeof(unsigned) * (2 * (size_t)(n_bounces + 2) + 1), 256);
+  const size_t ctr_bytes = WF_MAX_GROUPS * ctr_one; /* per plane group (stream) */
   size_t sort_tmp_bytes = 0;
   if (sort_mode)
   {
@@ -937,6 +940,7 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   unsigned *counts = reinterpret_cast<unsigned *>(p);            /* [n_bounces + 2] queue lengths */
   unsigned *fetch = counts + (n_bounces + 2);                    /* [n_bounces + 2] trace fetch cursors */
   unsigned *overflow = fetch + (n_bounces + 2);                  /* SPLIT: a queue ran out of entries */
+  char *const ctr_base = p; /* group g: its counts and fetch cursors at ctr_base + g * ctr_one */
   p += ctr_bytes;
   if (split)
   {
@@ -966,8 +970,6 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
   RTB_CUDA(cudaMemsetAsync(planes, 0, slots * 16, stream));
 
   const int shade_blocks = sm_count * 16;
-  const long long gen_warps = (long long)A.n_tiles * A.splits;
-  const int gen_blocks = (int)((gen_warps * 32 + 255) / 256);
 
   /* per-kernel timing (only with counters): events around every trace launch */
   struct EventList : std::vector<cudaEvent_t> /* destroyed on every return path */
@@ -986,55 +988,130 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
     cudaEventRecord(e, stream);
     ev.push_back(e);
   };
+  /* Two groups of planes, each with its own queues and its own stream: the persistent kernels of one group
+   * drain (their last warps finishing the longest rays) while the other group's next kernel fills the SMs that
+   * become free.  A path slot belongs to one group, so the order of additions per slot -- and the result, bit
+   * for bit -- is that of the one-stream schedule.  Not with per-kernel timing, the split estimator, ray sorting
+   * or the ray-pool kernel (one set of their buffers). */
+  int n_groups = (!phase_ms && !split && !sort_mode && !pool) ? 2 : 1;
+  if (const char *e = getenv("RTB_WF_STREAMS"))
+    n_groups = (!phase_ms && !split && !sort_mode && !pool) ? atoi(e) : 1;
+  n_groups = std::max(1, std::min(std::min(n_groups, WF_MAX_GROUPS), A.splits));
+  for (int g = 1; g < n_groups; g++)
+    if (!scene->wf_streams[g])
+    {
+      /* the streams are made once per device and kept (render() makes a new scene per call); the events are the scene's */
+      static std::mutex stream_mutex;
+      static cudaStream_t device_streams[64][WF_MAX_GROUPS] = {};
+      const int dev = scene->device & 63;
+      {
+        std::lock_guard<std::mutex> lock(stream_mutex);
+        if (!device_streams[dev][g])
+          RTB_CUDA(cudaStreamCreateWithFlags(&device_streams[dev][g], cudaStreamNonBlocking));
+        scene->wf_streams[g] = device_streams[dev][g];
+      }
+      RTB_CUDA(cudaEventCreateWithFlags(&scene->wf_joins[g], cudaEventDisableTiming));
+      if (!scene->wf_fork)
+        RTB_CUDA(cudaEventCreateWithFlags(&scene->wf_fork, cudaEventDisableTiming));
+    }
+  const int last_len = (A.s_end - A.s_begin) - (A.splits - 1) * A.chunk; /* samples of the (shorter) last plane */
+  struct Group
+  {
+    cudaStream_t stream;
+    RenderArgs A;
+    WfQueue q[2];
+    unsigned *counts, *fetch;
+    int planes, gen_blocks;
+    bool has_last;
+  } G[WF_MAX_GROUPS];
+  for (int g = 0; g < n_groups; g++)
+  {
+    Group &R = G[g];
+    R.stream = g == 0 ? stream : scene->wf_streams[g];
+    R.A = A;
+    R.A.plane_base = (int)((long long)A.splits * g / n_groups);
+    R.planes = (int)((long long)A.splits * (g + 1) / n_groups) - R.A.plane_base;
+    R.has_last = g == n_groups - 1;
+    const size_t first_slot = (size_t)R.A.plane_base * n_px;
+    for (int k = 0; k < 2; k++)
+    {
+      R.q[k] = q[k];
+      R.q[k].o_xy += first_slot; R.q[k].oz_dx += first_slot; R.q[k].d_yz += first_slot;
+      R.q[k].path += first_slot; R.q[k].hit += first_slot;
+      if (R.q[k].branch) R.q[k].branch += first_slot;
+      R.q[k].cap = n_groups == 1 ? (unsigned)cap : (unsigned)((size_t)R.planes * n_px);
+    }
+    R.counts = reinterpret_cast<unsigned *>(ctr_base + (size_t)g * ctr_one);
+    R.fetch = R.counts + (n_bounces + 2);
+    R.gen_blocks = (int)(((long long)A.n_tiles * R.planes * 32 + 255) / 256);
+  }
+  if (n_groups > 1)
+  {
+    RTB_CUDA(cudaEventRecord(scene->wf_fork, stream)); /* the planes are zeroed, the scene is built */
+    for (int g = 1; g < n_groups; g++)
+      RTB_CUDA(cudaStreamWaitEvent(scene->wf_streams[g], scene->wf_fork, 0));
+  }
   for (int wave = 0; wave < A.chunk; wave++)
   {
-    RTB_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), stream));
-    /* planes whose sub-range still has a sample number `wave`: all, or all but the (shorter) last */
-    const int last_len = (A.s_end - A.s_begin) - (A.splits - 1) * A.chunk;
-    const int n_valid_planes = wave < last_len ? A.splits : A.splits - 1;
-    k_wf_generate<<<gen_blocks, 256, 0, stream>>>(A, wave, n_valid_planes, q[0], &counts[0]);
-    launches++;
-    for (int b = 0; b < n_bounces; b++)
+    for (int g = 0; g < n_groups; g++)
     {
-      const WfQueue &qi = q[b & 1], &qo = q[(b + 1) & 1];
-      const bool sorted_in = sort_mode && b >= sort_from && b <= sort_until;        /* queue b was sorted */
-      const bool sort_out = sort_mode && b + 1 >= sort_from && b + 1 <= sort_until && b + 1 < n_bounces;
-      const unsigned *use_perm = sorted_in ? perm : nullptr;
-      mark();
-      if (pool)
-        launch_trace_pool(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, pool_stacks,
-                          (desc->reserved & 0xFF00) ? std::min(std::max(node_exit, 1), 32) : 32);
-      else
-      switch (variant)
-      {
-      case 2: launch_trace<2>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 22: launch_trace<22>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 54: launch_trace<54>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 86: launch_trace<86>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 150: launch_trace<150>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 182: launch_trace<182>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 214: launch_trace<214>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 10: launch_trace<10>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      case 6: launch_trace<6>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      default: launch_trace<0>(stats, sm_count, stream, A.sv, qi, &counts[b], &fetch[b], A.counters, refill_idle, node_exit, use_perm); break;
-      }
-      mark();
-      if (sort_out) /* slots beyond the queue's end keep the largest key and sort to the back */
-        RTB_CUDA(cudaMemsetAsync(keys, 0xFF, slots * 4, stream));
-      if (split)
-        k_wf_shade<true><<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes, nullptr, 0, overflow);
-      else
-        k_wf_shade<false><<<shade_blocks, 128, 0, stream>>>(A, wave, b, qi, &counts[b], qo, &counts[b + 1], planes,
-                                                            sort_out ? keys : nullptr, sort_mode, nullptr);
-      launches += 2;
-      if (sort_out)
-      {
-        size_t tmp = sort_tmp_bytes;
-        cub::DeviceRadixSort::SortPairs(sort_tmp, tmp, keys, keys_sorted, iota, perm, (int)slots, 0, 24, stream);
-        launches += 4;
-      }
+      Group &R = G[g];
+      RTB_CUDA(cudaMemsetAsync(R.counts, 0, sizeof(unsigned) * 2 * (size_t)(n_bounces + 2), R.stream));
+      /* planes whose sub-range still has a sample number `wave`: all, or all but the last */
+      const int n_valid_planes = (R.has_last && wave >= last_len) ? R.planes - 1 : R.planes;
+      k_wf_generate<<<R.gen_blocks, 256, 0, R.stream>>>(R.A, wave, n_valid_planes, R.q[0], &R.counts[0]);
+      launches++;
     }
+    for (int b = 0; b < n_bounces; b++)
+      for (int g = 0; g < n_groups; g++)
+      {
+        Group &R = G[g];
+        cudaStream_t st = R.stream;
+        unsigned *cnt = R.counts, *fch = R.fetch;
+        const WfQueue &qi = R.q[b & 1], &qo = R.q[(b + 1) & 1];
+        const bool sorted_in = sort_mode && b >= sort_from && b <= sort_until;        /* queue b was sorted */
+        const bool sort_out = sort_mode && b + 1 >= sort_from && b + 1 <= sort_until && b + 1 < n_bounces;
+        const unsigned *use_perm = sorted_in ? perm : nullptr;
+        mark();
+        if (pool)
+          launch_trace_pool(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, pool_stacks,
+                            (desc->reserved & 0xFF00) ? std::min(std::max(node_exit, 1), 32) : 32);
+        else
+        switch (variant)
+        {
+        case 2: launch_trace<2>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 22: launch_trace<22>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 54: launch_trace<54>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 86: launch_trace<86>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 150: launch_trace<150>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 182: launch_trace<182>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 214: launch_trace<214>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 10: launch_trace<10>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        case 6: launch_trace<6>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        default: launch_trace<0>(stats, sm_count, st, A.sv, qi, &cnt[b], &fch[b], A.counters, refill_idle, node_exit, use_perm); break;
+        }
+        mark();
+        if (sort_out) /* slots beyond the queue's end keep the largest key and sort to the back */
+          RTB_CUDA(cudaMemsetAsync(keys, 0xFF, slots * 4, st));
+        if (split)
+          k_wf_shade<true><<<shade_blocks, 128, 0, st>>>(R.A, wave, b, qi, &cnt[b], qo, &cnt[b + 1], planes, nullptr, 0, overflow);
+        else
+          k_wf_shade<false><<<shade_blocks, 128, 0, st>>>(R.A, wave, b, qi, &cnt[b], qo, &cnt[b + 1], planes,
+                                                          sort_out ? keys : nullptr, sort_mode, nullptr);
+        launches += 2;
+        if (sort_out)
+        {
+          size_t tmp = sort_tmp_bytes;
+          cub::DeviceRadixSort::SortPairs(sort_tmp, tmp, keys, keys_sorted, iota, perm, (int)slots, 0, 24, st);
+          launches += 4;
+        }
+      }
     RTB_CUDA(cudaGetLastError());
+  }
+  for (int g = 1; g < n_groups; g++)
+  {
+    RTB_CUDA(cudaEventRecord(scene->wf_joins[g], scene->wf_streams[g]));
+    RTB_CUDA(cudaStreamWaitEvent(stream, scene->wf_joins[g], 0));
   }
   k_wf_sum_planes<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(planes, A.splits, (unsigned)n_px, d_accum);
   RTB_CUDA(cudaGetLastError());

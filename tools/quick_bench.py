@@ -12,7 +12,8 @@ def run(name, source, W, H, spp, depth, reps=2, kernel=0, tune=0, planes=0, tune
     sc = api.Scene(source)
     info = sc.info
     t_build = time.time() - t0
-    desc = api.make_desc(W, H, 0, spp, max_depth=depth, kernel=kernel, tune=tune, planes=planes, tune2=tune2)
+    desc = api.make_desc(W, H, 0, spp, max_depth=depth, kernel=kernel, tune=tune, planes=planes, tune2=tune2,
+                         profile=int(os.environ.get("RTB_QB_PROFILE", "1")))  # 0: no per-kernel events, no node counts
     best = None
     for r in range(reps):
         fb, acc, ctr = sc.render(cam, desc, want_accum=False)
