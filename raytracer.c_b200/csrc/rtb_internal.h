@@ -135,9 +135,8 @@ struct rtb_scene_shard
 /* in-place all-gather (chunk `rank` of each array is this rank's) of the marshalled triangle records,
  * their boxes and (optionally) texture coordinates, on the legacy default stream of the current device */
 int rtb_shard_allgather(const rtb_scene_shard *shard, void *prims, size_t prim_chunk_bytes, void *box_lo, void *box_hi,
-                        size_t box_chunk_bytes, void *tex_or_null, size_t tex_chunk_bytes);
+                        size_t box_chunk_bytes, void *tex_or_null, size_t tex_chunk_bytes, int *d_flag_max_or_null);
 int rtb_shard_allgather_bytes(const rtb_scene_shard *shard, void *base, size_t chunk_bytes);
-int rtb_shard_max_int(const rtb_scene_shard *shard, int *d_value); /* in place: max over the ranks */
 int rtb_scene_create_sharded(const void *objects, size_t n_objects, int kind, int device, unsigned flags,
                              const rtb_scene_shard *shard, rtb_scene **out);
 

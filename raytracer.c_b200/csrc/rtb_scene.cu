@@ -742,6 +742,55 @@ cudaError_t upload_pageable(int device, void *dst, const void *src, size_t bytes
 }
 } // namespace
 
+/* The build reads a few words back (scene box, tree depth, node count, flags).  Into pageable memory every such
+ * copy is a host wait in the middle of the build; into a page-locked block they are asynchronous, and the whole
+ * build -- ~90 launches -- is enqueued behind the upload without the GPU ever waiting for the host. */
+struct BuildReadback
+{
+  BuildParams bp;
+  int levels[RTB_STACK_SIZE + 2];
+  int misc[2];
+  int nodes4;
+  int inexact;
+};
+
+namespace
+{
+std::mutex g_readback_mutex;
+std::vector<BuildReadback *> g_readback_free;
+
+struct ReadbackLease
+{
+  BuildReadback *p = nullptr;
+  ReadbackLease()
+  {
+    {
+      std::lock_guard<std::mutex> lock(g_readback_mutex);
+      if (!g_readback_free.empty())
+      {
+        p = g_readback_free.back();
+        g_readback_free.pop_back();
+      }
+    }
+    if (!p && cudaHostAlloc(reinterpret_cast<void **>(&p), sizeof(BuildReadback), cudaHostAllocPortable) != cudaSuccess)
+    {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    if (p)
+      memset(p, 0, sizeof(*p));
+  }
+  ~ReadbackLease()
+  {
+    if (p)
+    {
+      std::lock_guard<std::mutex> lock(g_readback_mutex);
+      g_readback_free.push_back(p);
+    }
+  }
+};
+} // namespace
+
 template <typename T>
 struct DevBuf
 {
@@ -984,7 +1033,14 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   DevBuf<float2> d_tex_unsorted;
   DevBuf<double> d_tri64_unsorted; /* triangle vertices as given; kept only if some are not float-representable */
   DevBuf<int> d_inexact;
-  int h_inexact = 0;
+  ReadbackLease lease; /* page-locked: the read-backs below never make the host wait */
+  if (!lease.p)
+  {
+    rtb_set_error("no page-locked memory for the build's read-back block");
+    return RTB_ENOMEM;
+  }
+  BuildReadback &rb = *lease.p;
+  int &h_inexact = rb.inexact;
   DevBuf<RefVertex> d_stage;
   DevBuf<unsigned> d_bounds, d_vals, d_vals_sorted;
   DevBuf<BuildParams> d_bp;
@@ -993,11 +1049,10 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   DevBuf<int2> d_children;
   DevBuf<int> d_parent_inner, d_parent_leaf, d_first, d_flags, d_misc, d_misc4, d_level_counts;
   DevBuf<int2> d_items_a, d_items_b;
-  int h_levels[RTB_STACK_SIZE + 2] = { 0 };
-  BuildParams h_bp;
-  memset(&h_bp, 0, sizeof(h_bp));
-  int h_misc[2] = { 0, 0 };
-  int h_nodes4 = 0;
+  int *const h_levels = rb.levels;
+  BuildParams &h_bp = rb.bp;
+  int *const h_misc = rb.misc;
+  int &h_nodes4 = rb.nodes4;
   bool bvh4_ok = true;
 
   if (N > 0)
@@ -1075,24 +1130,14 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
       }
       if (sharded)
       {
+        /* one NCCL group: the four gathers and the max of the "needs doubles" flag; no host wait */
         int grc = rtb_shard_allgather(shard, d_unsorted.p + n_bs, sizeof(PrimRec) * tri_chunk, d_lo.p + n_bs, d_hi.p + n_bs,
                                       sizeof(float4) * tri_chunk, want_tex ? d_tex_unsorted.p + 3 * n_bs : nullptr,
-                                      sizeof(float2) * 3 * tri_chunk);
+                                      sizeof(float2) * 3 * tri_chunk, d_inexact.p);
         if (grc != RTB_OK)
           return grc;
-        /* double-precision vertices travel only if some rank found a coordinate that needs them */
-        grc = rtb_shard_max_int(shard, d_inexact.p);
-        if (grc != RTB_OK)
-          return grc;
-        RTB_CUDA(cudaMemcpy(&h_inexact, d_inexact.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (h_inexact)
-        {
-          grc = rtb_shard_allgather_bytes(shard, d_tri64_unsorted.p + 9 * n_bs, sizeof(double) * 9 * tri_chunk);
-          if (grc != RTB_OK)
-            return grc;
-        }
       }
-      else if (n_tris)
+      if (n_tris)
         RTB_CUDA(cudaMemcpyAsync(&h_inexact, d_inexact.p, sizeof(int), cudaMemcpyDeviceToHost, 0));
     }
 
@@ -1182,8 +1227,9 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
         k_emit4_seed<<<1, 1>>>(eq);
         /* a BVH4 level consumes at least one BVH2 level; an empty level costs an empty launch */
         const int half_blocks = (int)((N / 2 + T) / T);
-        /* (a tree over N primitives has fewer than N levels: small scenes skip the empty launches) */
-        const int max_levels = (int)std::min<size_t>(RTB_STACK_SIZE, N);
+        /* (a tree over N primitives has fewer than N levels: small scenes skip the empty launches; a BVH4 deeper
+         * than (RTB_STACK_SIZE - 2) / 3 levels is not walked anyway -- see bvh4_ok below -- so it is not finished) */
+        const int max_levels = (int)std::min<size_t>((RTB_STACK_SIZE - 2) / 3 + 2, N);
         for (int level = 0; level < max_levels; level++)
           k_emit4<<<half_blocks, T>>>(d_vals_sorted.p, d_lo.p, d_hi.p, (int)N, d_children.p, d_first.p, d_node_lo.p,
                                       d_node_hi.p, d_bp.p, sc->d_nodes4, sc->d_nodes4q, eq, level, leaf_max,
@@ -1215,6 +1261,15 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   {
     /* some mesh coordinate is not float-representable (a mesh transformed in double, main.c:140-147): keep the
      * caller's doubles, in BVH order, for the exact triangle test and the surface normal */
+    if (shard != nullptr && shard->n_ranks > 1 && n_tris >= (size_t)shard->n_ranks * 4096)
+    {
+      /* sharded upload: every rank holds the doubles of its own triangles only (the flag is the max over the ranks,
+       * so all of them are here) */
+      const size_t chunk = (n_tris + (size_t)shard->n_ranks - 1) / (size_t)shard->n_ranks;
+      int grc = rtb_shard_allgather_bytes(shard, d_tri64_unsorted.p + 9 * n_bs, sizeof(double) * 9 * chunk);
+      if (grc != RTB_OK)
+        return grc;
+    }
     RTB_CUDA(scene_alloc(sc.get(), &sc->d_tri64, 9 * (N + 1)));
     RTB_CUDA(cudaMemsetAsync(sc->d_tri64 + 9 * N, 0, sizeof(double) * 9, 0)); /* the degenerate triangle of empty slots */
     k_reorder64<<<(int)((N + 255) / 256), 256>>>(d_vals_sorted.p, (int)N, d_tri64_unsorted.p, sc->d_tri64);
