@@ -22,6 +22,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cfloat>
 #include <cstdlib>
@@ -966,6 +968,17 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   RTB_CUDA(cudaEventCreate(&ev0));
   RTB_CUDA(cudaEventCreate(&ev1));
   RTB_CUDA(cudaEventRecord(ev0, 0));
+  /* development aid ($RTB_TIMING): where the build spends its time; the marks synchronise, so the sum is longer
+   * than an unobserved build */
+  const bool timing = getenv("RTB_TIMING") != nullptr;
+  std::vector<std::pair<const char *, double>> marks;
+  auto mark = [&](const char *what) {
+    if (!timing)
+      return;
+    cudaStreamSynchronize(0);
+    marks.emplace_back(what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count());
+  };
+  mark("start");
 
   /* development knobs (documented in DESIGN.md): leaf size and oversized-primitive ratio */
   /* measured on B200 (profiles/r1_tuning.md): sphere scenes are fastest with one sphere per
@@ -1128,6 +1141,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
         }
         tri_first += m.n_tris;
       }
+      mark("upload + marshal");
       if (sharded)
       {
         /* one NCCL group: the four gathers and the max of the "needs doubles" flag; no host wait */
@@ -1139,6 +1153,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
       }
       if (n_tris)
         RTB_CUDA(cudaMemcpyAsync(&h_inexact, d_inexact.p, sizeof(int), cudaMemcpyDeviceToHost, 0));
+      mark("all-gather");
     }
 
     /* scene box -> guard box, padding, Morton grid (all on the device) */
@@ -1254,6 +1269,19 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   }
   RTB_CUDA(cudaEventRecord(ev1, 0));
   RTB_CUDA(cudaEventSynchronize(ev1)); /* the only host wait of the build */
+  mark("sort + hierarchy + BVH4");
+  if (timing)
+  {
+    std::string line = "rtb_scene_create";
+    if (shard) line += " rank " + std::to_string(shard->rank);
+    for (size_t k = 1; k < marks.size(); k++)
+    {
+      char buf[96];
+      snprintf(buf, sizeof(buf), "%s %s %.2f ms", k == 1 ? ":" : ",", marks[k].first, marks[k].second - marks[k - 1].second);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+  }
   float ms = 0;
   RTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
 

@@ -91,3 +91,54 @@ def test_drop_in_render_uses_the_whole_box(gpu_api):
         host.render_ex(fb.ctypes.data, objs.ctypes.data, len(objs), C.byref(cam), C.byref(opt), C.byref(rp))
         frames.append(fb)
     assert np.abs(frames[0].astype(int) - frames[1].astype(int)).max() <= 1
+
+
+_RANK_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import __graft_entry__ as entry
+pkg = entry.load_package(); api = pkg.api
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+idt = torch.zeros(api.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+dist.broadcast(idt, src=0)
+comm = api.Comm.rank(bytes(idt.cpu().numpy().tobytes()), rank, world, local)
+W, H, SPP = 128, 72, 6
+verts = api.heightfield_mesh(96, 20 * W / H * 0.98)
+holder = api.mesh_room(verts, W, H)
+cam = api.init_camera(W, H)
+desc = api.make_desc(W, H, 0, SPP, max_depth=5)
+fb, acc, ctr = comm.render_host(holder, cam, desc, want_accum=True)
+if rank == 0:
+    with api.Scene(holder, device=local) as sc:
+        fb0, acc0, c0 = sc.render(cam, desc, want_accum=True)
+    assert ctr.rays == c0.rays and ctr.paths == W * H * SPP, (ctr.rays, c0.rays)
+    np.testing.assert_allclose(acc, acc0, rtol=2e-5, atol=1e-5)
+    assert np.abs(fb.astype(int) - fb0.astype(int)).max() <= 1
+    print("OK", world, ctr.rays)
+dist.barrier()
+comm.close()
+dist.destroy_process_group()
+"""
+
+
+def test_one_process_per_gpu_group(gpu_api, tmp_path):
+    """the torchrun form (rtb_comm_create_rank, id broadcast by the launcher): two processes, two GPUs,
+    rtb_render_multi == the one-GPU frame of the same job"""
+    _need(gpu_api, 2)
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "rank_worker.py"
+    script.write_text(_RANK_WORKER.format(root=root))
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "OK 2" in r.stdout

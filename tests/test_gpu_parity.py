@@ -393,3 +393,20 @@ def test_many_oversized_spheres(gpu_api):
         _, acc, ctr = sc.render(cam, gpu_api.make_desc(W, H, 0, 2), want_accum=True)
     _assert_hits_equal(bvh, brute, "48 oversized spheres")
     assert np.isfinite(acc).all() and ctr.rays > 0
+
+
+def test_counters_are_deterministic_when_many_rays_skip_the_walk(gpu_api):
+    """a lane refilled with a ray that needs no walk (it misses the guard box of a small tree inside a
+    big-list room) used to fetch a duplicate ray in the same refill; the image was unaffected, the primitive-test
+    counter was double-counted and depended on scheduling.  Equal counters run to run, and equal to the ray-pool
+    kernel's (same tree, same tests, different scheduling)."""
+    W, H = 160, 90
+    objs = gpu_api.scene_default(W, H)[:12].copy()          # the six walls + a few spheres: most rays miss the tree
+    objs["radius"][6:] *= 0.25
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        runs = [sc.render(cam, gpu_api.make_desc(W, H, 0, 8, max_depth=5), want_accum=True) for _ in range(3)]
+        pool = sc.render(cam, gpu_api.make_desc(W, H, 0, 8, max_depth=5, tune=(1024 << 16) | (16 << 8)), want_accum=True)
+    for fb, acc, c in runs[1:] + [pool]:
+        assert c.prim_tests == runs[0][2].prim_tests and c.rays == runs[0][2].rays
+        assert np.array_equal(acc, runs[0][1])
