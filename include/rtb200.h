@@ -128,7 +128,7 @@ int rtb_scene_info_get(const rtb_scene *scene, rtb_scene_info *info);
 void rtb_scene_destroy(rtb_scene *scene);
 
 /* A destroyed scene parks its device buffers (scene arrays and the wavefront kernels' ray queues, up
- * to 11.7 GB) in a per-device cache and the next scene reuses them, so that render() -- one scene per
+ * to 23.4 GB) in a per-device cache and the next scene reuses them, so that render() -- one scene per
  * call -- allocates nothing in steady state.  This returns everything cached for `device` to the driver. */
 void rtb_release_workspace(int device);
 

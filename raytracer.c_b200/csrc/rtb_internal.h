@@ -116,7 +116,7 @@ struct rtb_scene
 };
 
 /* Per-device cache of device buffers.  render() creates and destroys a scene per call; sending
- * ~13 buffers (0.3 GB of scene arrays, up to 11.7 GB of ray queues) through the CUDA memory pool
+ * ~13 buffers (0.1 GB of scene arrays, up to 23.4 GB of ray queues) through the CUDA memory pool
  * on every call made the call time erratic: the pool re-grows whenever its free blocks get carved
  * up differently, and a fresh allocation costs 0.1-1.5 s on this platform (measured:
  * scene create 4 ms typically, 20-1500 ms on every third call).  A destroyed scene parks its

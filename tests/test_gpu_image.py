@@ -153,7 +153,7 @@ def test_workspace_is_reused_across_scenes(gpu_api):
 
 
 def test_wave_shrinks_when_memory_is_short(gpu_api):
-    """the ray queues want up to 11.7 GB; with little free memory the render must still succeed
+    """the ray queues want up to 23.4 GB; with little free memory the render must still succeed
     (smaller waves), and give the same image up to float summation order"""
     import torch
     W, H, SPP = 1920, 1080, 32
