@@ -150,14 +150,14 @@ def measured_peaks():
 
 
 def ncu_traffic(workload):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the AVERAGE k_wf_trace launch, from the
-    committed ncu launch list of the same command (profiles/ncu_traffic.json), if any"""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the k_wf_trace launches PER INTERSECTED RAY, from
+    the committed ncu launch list of the same command (profiles/ncu_traffic.json), if any"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
         if d.get("kernel") == "k_wf_trace":
-            return d.get(workload + "_per_launch")
+            return d.get(workload + "_bytes_per_intersected_ray")
     return None
 
 
@@ -476,9 +476,10 @@ def main_gpu(args):
             l2_gbs = hit_rank * bytes_ray / sec / 1e9
             hbm_gbs = hit_rank * HBM_BYTES_RAY / sec / 1e9
             tflops = hit_rank * flops_ray / sec / 1e12
-            traffic_launch = ncu_traffic(args.workload)  # per launch
-            traffic = traffic_launch * trace_launches if traffic_launch else None  # per step
             per_launch = 1.0 / max(1, trace_launches)
+            traffic_ray = ncu_traffic(args.workload)  # DRAM bytes per intersected ray (ncu)
+            traffic = traffic_ray * hit_rank if traffic_ray else None  # per step
+            traffic_launch = traffic * per_launch if traffic else None
             roofline = {
                 # what bounds the kernel is neither HBM nor the tensor cores (north_star: not a dense contraction):
                 # its algorithmic bytes are BVH-node and primitive fetches served by L1/L2, so the denominator is L2
@@ -486,7 +487,7 @@ def main_gpu(args):
                 "frac": l2_gbs / l2_peak if l2_peak else None,
                 "peak_source": "measured in this run: rtb_probe_l2_bandwidth, 32 MB L2-resident buffer, ld.global.cg.v4 from all SMs",
                 "traffic": traffic_launch,
-                "traffic_def": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from the committed ncu launch list of this command (profiles/ncu_traffic.json)",
+                "traffic_def": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the average launch: ncu's bytes per intersected ray over all k_wf_trace launches of this command (profiles/ncu_traffic.json, profiles/r2_launches_c3.csv) x the rays of the average launch",
                 "bytes_per_launch": hit_rank * bytes_ray * per_launch, "avg_launch_ms": trace_ms * per_launch,
                 "launches_per_step": trace_launches, "kernel_ms_per_step": trace_ms, "share_of_step": trace_share,
                 "bytes_per_intersected_ray": bytes_ray, "intersected_rays_per_step": hit_rank,
