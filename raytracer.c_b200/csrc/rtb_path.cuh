@@ -204,7 +204,7 @@ __device__ __forceinline__ void path_shade(const RenderArgs &A, PathState &st, c
 int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, float *d_accum, cudaStream_t stream,
               bool stats, unsigned long long &launches, float *phase_ms);
 
-/* rtb_whitted.cu: the cast_ray integrator, one launch */
-int whitted_render(rtb_scene *scene, RenderArgs &A, float *d_accum, cudaStream_t stream, unsigned long long &launches);
+/* rtb_whitted.cu: the cast_ray integrator, one launch; writes A.splits planes to A.out (summed by the caller) */
+int whitted_render(rtb_scene *scene, RenderArgs &A, cudaStream_t stream, unsigned long long &launches);
 
 #endif /* RTB_PATH_CUH */

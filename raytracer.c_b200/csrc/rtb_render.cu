@@ -670,7 +670,8 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
    * out of 180 GB): the deep bounces then still have enough rays to fill 148 SMs and the tail of one
    * group's persistent kernel is covered by the other group's next kernel (measured C3, round 2: 32 M
    * 4.19, 64 M 4.29, 128 M 4.35 Grays/s); never more than a quarter of the free device memory. */
-  const bool wavefront = desc->kernel == 6 || desc->kernel == 0;
+  const bool whitted = desc->integrator == RTB_INTEGRATOR_WHITTED;
+  const bool wavefront = (desc->kernel == 6 || desc->kernel == 0) && !whitted;
   if (!wavefront && desc->integrator == RTB_INTEGRATOR_PATH && scene->view.nodes == nullptr && scene->view.root_ref >= 0 &&
       scene->view.root_ref != RTB_REF_NONE)
   {
@@ -739,13 +740,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
   }
   else
   {
-    if (desc->integrator == RTB_INTEGRATOR_WHITTED)
-    {
-      int wrc = whitted_render(scene, A, d_accum, stream, launches);
-      if (wrc != RTB_OK)
-        return wrc;
-    }
-    else if (wavefront)
+    if (wavefront)
     {
       int wrc = wf_render(scene, A, desc, d_accum, stream, counters != nullptr && desc->profile != 0, launches,
                           (counters && desc->profile != 0) ? phase_ms : nullptr);
@@ -784,6 +779,14 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
     const int threads = 128;
     const long long warps = (long long)A.n_tiles * splits;
     const int blocks = (int)((warps * 32 + threads - 1) / threads);
+    if (whitted)
+    {
+      /* cast_ray: one thread per (plane, pixel), like the megakernels */
+      int wrc = whitted_render(scene, A, stream, launches);
+      if (wrc != RTB_OK)
+        return wrc;
+    }
+    else
     /* desc->kernel: 0/1 megakernel (default), 2 warp-scheduled state machine (+FP32 sphere
      * pre-test), 3 megakernel + FP32 sphere pre-test.  See DESIGN.md "Kernel choice". */
     switch (desc->kernel)

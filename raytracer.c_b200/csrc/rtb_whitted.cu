@@ -185,17 +185,22 @@ __device__ d3 whitted_cast(const SceneView &sv, const d3 &o0, const d3 &d0, int 
   }
 }
 
-/* one thread per pixel: sum over the call's samples, jitter as in path_begin (same Philox words,
- * so the primary rays are those of the path tracer) */
-__global__ void __launch_bounds__(64) k_whitted_render(const __grid_constant__ RenderArgs A, float *__restrict__ out)
+/* one thread per (plane, pixel): sum over the plane's samples, jitter as in path_begin (same Philox words, so the
+ * primary rays are those of the path tracer).  Planes = contiguous sample sub-ranges, summed in order by the
+ * caller (k_sum_planes): small frames still fill the GPU (C1 is 57 600 pixels, a B200 holds 300 000 threads). */
+__global__ void __launch_bounds__(64) k_whitted_render(const __grid_constant__ RenderArgs A)
 {
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_px = A.width * A.height;
+  const int plane = (int)(tid / n_px);
+  const int pix = (int)(tid - (long long)plane * n_px);
   unsigned long long rays = 0, paths = 0;
-  if (pix < A.width * A.height)
+  if (plane < A.splits)
   {
     const int x = pix % A.width, y = pix / A.width;
+    const int s0 = A.s_begin + plane * A.chunk, s1 = min(A.s_end, s0 + A.chunk);
     d3 sum = d3_make(0, 0, 0);
-    for (int s = A.s_begin; s < A.s_end; s++)
+    for (int s = s0; s < s1; s++)
     {
       PathState st;
       path_begin(A, st, x, y, (unsigned)pix, (unsigned)s);
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(64) k_whitted_render(const __grid_constant__ R
       sum = d3_add(sum, c);
       paths++;
     }
+    float *out = A.out + (size_t)plane * 3 * n_px;
     out[3 * (size_t)pix + 0] = (float)sum.x;
     out[3 * (size_t)pix + 1] = (float)sum.y;
     out[3 * (size_t)pix + 2] = (float)sum.z;
@@ -236,17 +242,17 @@ __global__ void __launch_bounds__(64) k_cast_rays(const __grid_constant__ SceneV
     ray_counts[i] = rays;
 }
 
-int whitted_render(rtb_scene *scene, RenderArgs &A, float *d_accum, cudaStream_t stream, unsigned long long &launches)
+int whitted_render(rtb_scene *scene, RenderArgs &A, cudaStream_t stream, unsigned long long &launches)
 {
   if (A.max_depth > WH_MAX_DEPTH)
   {
     rtb_set_error("Whitted integrator: max_depth must be <= 15");
     return RTB_EINVAL;
   }
-  const size_t n_px = (size_t)A.width * A.height;
-  k_whitted_render<<<(unsigned)((n_px + 63) / 64), 64, 0, stream>>>(A, d_accum);
+  const size_t n_threads = (size_t)A.width * A.height * (size_t)A.splits;
+  k_whitted_render<<<(unsigned)((n_threads + 63) / 64), 64, 0, stream>>>(A);
   RTB_CUDA(cudaGetLastError());
-  launches++;
+  (void)launches; /* counted by the caller together with the plane sum */
   (void)scene;
   return RTB_OK;
 }
