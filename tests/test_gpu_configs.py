@@ -220,3 +220,30 @@ def test_drop_in_render_honours_dielectric_mode_and_total_samples(gpu_api):
     want = np.minimum(1.0, (acc_s.astype(np.float64) / (2 * SPP)) ** 0.2) * 255.0
     assert np.abs(fb_half.astype(int) - np.floor(want).astype(int)).max() <= 1
     assert fb_half.astype(int).sum() < fb_s.astype(int).sum()
+
+
+# ---- the named configs at their FULL frame sizes: size-independent properties ------------------------------
+
+@pytest.mark.parametrize("name,W,H,count,mix,depth", [
+    ("c2", 1920, 1080, 10000, (0.5, 0.2, 0.2), 8),
+    ("c4", 3840, 2160, 10000, (0.2, 0.4, 0.4), 8),
+    ("c5", 512, 512, 2000, (0.1, 0.9, 0.0), 64),
+])
+def test_full_frame_properties_of_the_sphere_configs(gpu_api, name, W, H, count, mix, depth):
+    """at BASELINE.json's frame sizes and depths (a few samples instead of hundreds): the sum over samples is
+    additive over sample ranges (what the multi-GPU sharding relies on), bit-reproducible, finite and non-negative;
+    ray counts add up; every path casts between 1 and depth + 2 rays; the frame is the tonemap of the sums"""
+    objs = gpu_api.scene_sphere_field(count, W, H, mix=mix)
+    cam = gpu_api.init_camera(W, H)
+    with gpu_api.Scene(objs) as sc:
+        fb, ab, cab = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=depth), want_accum=True)
+        _, a, ca = sc.render(cam, gpu_api.make_desc(W, H, 0, 2, max_depth=depth), want_accum=True)
+        _, b, cb = sc.render(cam, gpu_api.make_desc(W, H, 2, 4, max_depth=depth), want_accum=True)
+        fb2, ab2, cab2 = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=depth), want_accum=True)
+    assert np.array_equal(ab, ab2) and np.array_equal(fb, fb2) and cab.rays == cab2.rays  # idempotent
+    assert np.isfinite(ab).all() and (ab >= 0).all()
+    np.testing.assert_allclose(a + b, ab, rtol=1e-5, atol=1e-6)
+    assert ca.rays + cb.rays == cab.rays and cab.paths == W * H * 4
+    assert 1.0 <= cab.rays / cab.paths <= depth + 2
+    want = np.floor(255.0 * np.minimum(1.0, (ab.astype(np.float64) / 4) ** 0.2)).astype(int)
+    assert np.abs(fb.astype(int) - want).max() <= 1  # pow() in CUDA vs numpy at truncation boundaries
