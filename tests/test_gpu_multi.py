@@ -142,3 +142,29 @@ def test_one_process_per_gpu_group(gpu_api, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert "OK 2" in r.stdout
+
+
+def test_sharded_upload_of_double_precision_vertices(gpu_api):
+    """a mesh moved with apply_matrix (main.c:140-147) has genuine double coordinates: every rank finds out on its
+    own share, the flag is max-reduced inside the gather group, and the doubles are all-gathered too"""
+    _need(gpu_api, 2)
+    W, H, SPP = 128, 72, 4
+    verts = gpu_api.heightfield_mesh(96, 20 * W / H * 0.5)
+    a = 0.37
+    m = np.array([[np.cos(a), 0, np.sin(a), 0.1234567], [0, 1.1, 0, 1.0 / 3.0], [-np.sin(a), 0, np.cos(a), -0.7], [0, 0, 0, 1]])
+    gpu_api.apply_matrix(verts, m)
+    holder = gpu_api.mesh_room(verts, W, H)
+    cam = gpu_api.init_camera(W, H)
+    desc = gpu_api.make_desc(W, H, 0, SPP, max_depth=5)
+    with gpu_api.Scene(holder) as sc:
+        assert sc.info.double_triangles == 1
+        fb0, acc0, c0 = sc.render(cam, desc, want_accum=True)
+    with gpu_api.Comm.local(2) as comm:
+        fb1, acc1, c1 = comm.render_host(holder, cam, desc, want_accum=True)
+    assert c1.rays == c0.rays and c1.prim_tests == c0.prim_tests
+    np.testing.assert_allclose(acc1, acc0, rtol=2e-5, atol=1e-5)
+
+
+def test_more_gpus_than_the_box_has_is_an_error(gpu_api):
+    with pytest.raises(gpu_api.RtbError, match="device ordinal"):
+        gpu_api.Comm.local(gpu_api.device_count() + 1)
