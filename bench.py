@@ -337,7 +337,8 @@ def main_gpu(args):
     accum = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
-    desc = api.make_desc(W, H, 0, total_spp, max_depth=depth, seed=SEED, integrator=integrator)  # the WHOLE job
+    # the WHOLE job; profile=0: no per-kernel events, so the wavefront pipeline runs as it does in production (two streams)
+    desc = api.make_desc(W, H, 0, total_spp, max_depth=depth, seed=SEED, integrator=integrator, profile=0)
 
     def step(want_counters=False):
         """device-resident: accumulate (this rank's samples) -> one ncclReduce -> tonemap on rank 0"""
@@ -355,7 +356,8 @@ def main_gpu(args):
     # warm-up; the first pass, with counters, gives the (deterministic) whole-job ray count of a step
     ctr = step(want_counters=True)
     rays_step, hits_step = float(ctr.rays), float(ctr.rays_intersected)
-    node_visits, prim_tests = float(ctr.node_visits), float(ctr.prim_tests)
+    prim_tests = float(ctr.prim_tests)
+    node_visits_rank, hits_prof = 0.0, 1.0  # node visits are counted by the profiling pass below (rank 0's share)
     launches_per_step = int(ctr.launches) + (1 if world == 1 else 0)  # whole job (+ the tonemap launch)
     for _ in range(max(3, args.warmup)):
         step()
@@ -449,6 +451,7 @@ def main_gpu(args):
             step_ms_list.append(cc.gpu_ms)
             trace_launches = int(cc.trace_launches)
             hit_rank = float(cc.rays_intersected)
+            node_visits_rank, hits_prof = float(cc.node_visits), max(1.0, float(cc.rays_intersected))
     trace_ms = sum(trace_ms_list) / max(1, len(trace_ms_list))
     trace_share = trace_ms / (sum(step_ms_list) / len(step_ms_list)) if step_ms_list else None
     flops_ray, bytes_ray = algorithmic_cost(args.workload, n_prims or 38, S, P)
@@ -508,7 +511,7 @@ def main_gpu(args):
             "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
             "config": dict(workload_config(args.workload, total_spp, world, strong), integrator=args.integrator),
             "paths_per_s": paths_per_s, "rays_per_step": rays_step, "rays_per_path": rays_step / (W * H * total_spp),
-            "node_visits_per_ray": node_visits / max(1.0, hits_step), "prim_tests_per_ray": prim_tests / max(1.0, hits_step),
+            "node_visits_per_ray": node_visits_rank / hits_prof, "prim_tests_per_ray": prim_tests / max(1.0, hits_step),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(W * H * 3), "ms_per_call": [round(x, 2) for x in e2e_calls],
                     "host_memory": "pageable (malloc'ed by the caller, like the reference's main.c)",
