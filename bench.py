@@ -458,7 +458,8 @@ def main_gpu(args):
     hbm_peak, hbm_src = measured_peaks()
     l2_peak = api.probe_l2_bandwidth(32 << 20, 50, device=local) if rank == 0 else 0.0  # measured now, GB/s
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_nominal = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_peak = api.probe_fp32_tflops(4096, device=local) if rank == 0 else fp32_nominal  # measured now
     HBM_BYTES_RAY = 64 + 16  # queue entry read once (o, d as doubles + the seeded hit record) + the hit record written back
 
     line = None
@@ -501,7 +502,8 @@ def main_gpu(args):
                         "traffic_over_algorithmic": (traffic / (hit_rank * HBM_BYTES_RAY)) if traffic else None},
                 "fp32": {"bound": "fp32", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
                          "flops_per_intersected_ray": flops_ray,
-                         "peak_source": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (median clock under load)"},
+                         "peak_source": "measured in this run: rtb_probe_fp32_tflops (8 independent FFMA chains per thread, all SMs)",
+                         "nominal": fp32_nominal, "nominal_def": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (median clock under load)"},
                 "limiter": "issue slots and latency with 17 of 32 lanes active per instruction (profiles/r2_wf_trace_ncu.md): no memory level or pipe is saturated",
             }
         line = {

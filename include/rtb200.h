@@ -18,7 +18,7 @@
  *   rtb_cast_rays          cast_ray() for arbitrary rays (raytracer.c:556-641): parity probe of the
  *                          Whitted integrator (rtb_render_desc.integrator = RTB_INTEGRATOR_WHITTED)
  *   rtb_philox4x32_10      random_double()'s replacement (raytracer.c:227): KAT probe
- *   rtb_probe_l2_bandwidth no reference counterpart: measures the L2 roofline denominator
+ *   rtb_probe_l2_bandwidth, rtb_probe_fp32_tflops   no reference counterpart: measure the L2 and FP32 roofline denominators
  *   rtb_comm_*, rtb_render_multi   render() on all GPUs of the box: spp-sharded, ONE ncclReduce of the
  *                          float sums, sharded scene upload + all-gather (no reference counterpart:
  *                          upstream is `#pragma omp parallel for` over rows, raytracer.c:184)
@@ -206,6 +206,9 @@ int rtb_render_multi(rtb_comm *comm, const void *objects, size_t n_objects, int 
 /* measurement probe: read bandwidth of an L2-resident buffer of `bytes` (128-bit ld.global.cg from every SM,
  * `iters` passes), in GB/s -- the denominator bench.py uses for the walk's L1/L2-served algorithmic bytes */
 int rtb_probe_l2_bandwidth(size_t bytes, int iters, int device, float *gb_per_s);
+/* measurement probe: FP32 FMA throughput (8 independent chains per thread, every SM full), in TFLOP/s -- the
+ * denominator bench.py uses for the walk's algorithmic flops */
+int rtb_probe_fp32_tflops(int iters, int device, float *tflops);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ RTB_SYMBOLS = [
     "rtb_scene_create_objects_flags", "rtb_scene_create_flags",
     "rtb_scene_info_get", "rtb_scene_destroy", "rtb_release_workspace", "rtb_render_accum", "rtb_tonemap", "rtb_render",
     "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth", "rtb_cast_rays",
-    "rtb_render_mean", "rtb_comm_unique_id", "rtb_comm_create_rank", "rtb_comm_create_local", "rtb_comm_size",
+    "rtb_probe_fp32_tflops", "rtb_render_mean", "rtb_comm_unique_id", "rtb_comm_create_rank", "rtb_comm_create_local", "rtb_comm_size",
     "rtb_comm_local_ranks", "rtb_comm_destroy", "rtb_comm_shard_samples", "rtb_comm_scene_create", "rtb_comm_render", "rtb_render_multi",
 ]
 # the reference's exported surface (raytracer.h:135-164) plus the documented extensions
@@ -534,6 +534,15 @@ def probe_l2_bandwidth(nbytes=32 << 20, iters=50, device=0):
     cu, _ = load()
     out = C.c_float(0.0)
     _check(cu.rtb_probe_l2_bandwidth(nbytes, iters, device, C.byref(out)), "rtb_probe_l2_bandwidth")
+    return float(out.value)
+
+
+def probe_fp32_tflops(iters=4096, device=0):
+    """FP32 FMA throughput (TFLOP/s) measured on the device: the denominator for the walk's algorithmic flops"""
+    cu, _ = load()
+    out = C.c_float(0.0)
+    cu.rtb_probe_fp32_tflops.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
+    _check(cu.rtb_probe_fp32_tflops(iters, device, C.byref(out)), "rtb_probe_fp32_tflops")
     return float(out.value)
 
 

@@ -1048,6 +1048,58 @@ extern "C" int rtb_probe_l2_bandwidth(size_t bytes, int iters, int device, float
   return RTB_OK;
 }
 
+/* ---- FP32 FMA throughput probe: the denominator of the walk's algorithmic flops (SURVEY 8d asks for a measured
+ * FP32 peak as well) ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_probe_fp32(int iters, float seed, float *sink)
+{
+  /* 8 independent FMA chains per thread: enough ILP to keep the FMA pipe fed at 8 warps per scheduler */
+  float a0 = seed + threadIdx.x, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f,
+        a7 = a0 + 7.0f;
+  const float m = 0.999999f, c = 1e-7f;
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+    {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123456.789f)
+    *sink = r;
+}
+
+extern "C" int rtb_probe_fp32_tflops(int iters, int device, float *tflops)
+{
+  if (!tflops || iters < 1)
+  {
+    rtb_set_error("rtb_probe_fp32_tflops: bad argument");
+    return RTB_EINVAL;
+  }
+  RTB_CUDA(cudaSetDevice(device));
+  Dev<float> d_sink;
+  RTB_CUDA(cudaMalloc(&d_sink.p, sizeof(float)));
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  RTB_CUDA(cudaEventCreate(&e0));
+  RTB_CUDA(cudaEventCreate(&e1));
+  k_probe_fp32<<<blocks, threads>>>(iters / 8 + 1, 1.0f, d_sink.p); /* warm */
+  RTB_CUDA(cudaEventRecord(e0));
+  k_probe_fp32<<<blocks, threads>>>(iters, 1.0f, d_sink.p);
+  RTB_CUDA(cudaEventRecord(e1));
+  RTB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.0f;
+  RTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * threads;
+  *tflops = (float)(flops / (ms * 1e-3) / 1e12);
+  return RTB_OK;
+}
+
 extern "C" int rtb_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, size_t n, uint32_t *out4, int device)
 {
   if (!ctr4 || !key2 || !out4)
