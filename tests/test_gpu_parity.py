@@ -410,3 +410,52 @@ def test_counters_are_deterministic_when_many_rays_skip_the_walk(gpu_api):
     for fb, acc, c in runs[1:] + [pool]:
         assert c.prim_tests == runs[0][2].prim_tests and c.rays == runs[0][2].rays
         assert np.array_equal(acc, runs[0][1])
+
+
+@pytest.mark.parametrize("doubles", [False, True])
+def test_degenerate_and_duplicate_triangles(gpu_api, ol, abi, doubles):
+    """a mesh with exact duplicates of some triangles (equal t: the lower loop index must win, raytracer.c:404),
+    zero-area triangles (three equal vertices, collinear vertices: |det| < EPSILON, raytracer.c:134), a triangle
+    spanning the whole room and triangles 1e-5 across -- as floats and as genuine doubles (the tri64 path):
+    every walk returns the oracle's brute-force hit, primitive index included, and the accumulated frame
+    matches the oracle's"""
+    W, H = 96, 54
+    base = gpu_api.heightfield_mesh(30, 20 * W / H * 0.98)
+    pos = base["pos"].reshape(-1, 3, 3).copy()
+    rng = np.random.default_rng(99)
+    dup = pos[rng.integers(0, len(pos), 300)]                      # appended later: higher loop index
+    point = np.repeat(pos[rng.integers(0, len(pos), 50), :1], 3, axis=1)                    # v0 = v1 = v2
+    a, b = pos[rng.integers(0, len(pos), 50), 0], pos[rng.integers(0, len(pos), 50), 1]
+    collinear = np.stack([a, 0.5 * (a + b), b], axis=1)
+    huge = np.array([[[-60.0, 16.0, -40.0], [60.0, 16.0, -40.0], [0.0, 16.5, 45.0]]])      # above the ray origins
+    c = rng.uniform(-15, 15, (200, 1, 3)) * np.array([1.0, 0.2, 1.0]) + np.array([0.0, 2.0, 0.0])
+    tiny = c + rng.normal(size=(200, 3, 3)) * 1e-5
+    tris = np.concatenate([pos, dup, point, collinear, huge, tiny])
+    if doubles:
+        tris = tris * (1.0 + 2.0 ** -40) + 2.0 ** -30                                        # not float-representable
+    else:
+        tris = tris.astype(np.float32).astype(np.float64)
+    verts = np.zeros(3 * len(tris), dtype=abi.VERTEX_DTYPE)
+    verts["pos"] = tris.reshape(-1, 3)
+    verts["tex"] = rng.uniform(0, 1, (3 * len(tris), 2))
+    holder = gpu_api.mesh_room(verts, W, H)
+    # rays: random ones, and rays aimed at the duplicated, degenerate and tiny triangles
+    aim = np.concatenate([dup.mean(axis=1), dup[:, 0], point[:, 0], collinear[:, 1], tiny.mean(axis=1)])
+    o = rng.uniform(-20, 20, (len(aim), 3)) * np.array([1.0, 0.1, 1.0]) + np.array([0.0, 12.0, 0.0])
+    d = aim - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([random_rays_in_room(rng, 4000), np.concatenate([o, d], axis=1)])
+    want = ol.intersect_rays(holder, rays)
+    with gpu_api.Scene(holder, all_trees=True) as sc:
+        assert bool(sc.info.double_triangles) == doubles
+        for mode in (0, 1, 3, 4, 5):
+            _assert_hits_equal(sc.trace_rays(rays, use_bvh=mode), want, f"degenerate mesh, walk {mode}")
+        cam = gpu_api.init_camera(W, H)
+        _, acc, ctr = sc.render(cam, gpu_api.make_desc(W, H, 0, 4, max_depth=5), want_accum=True)
+    n_base = len(pos)
+    first = want["prims"][want["ids"] == 6] - 6          # triangle index inside the mesh (6 walls precede it)
+    assert ((first >= n_base) & (first < n_base + 300)).sum() == 0, "a duplicate (higher index) won a tie"
+    assert (first == n_base + 400).sum() > 100, "the room-spanning triangle must be hit"
+    ref_sum, (ref_rays, _) = ol.render_sum(holder, cam, W, H, 4, rng="philox", dielectric="stochastic", max_depth=5)
+    assert ctr.rays == ref_rays
+    np.testing.assert_allclose(acc, ref_sum, rtol=1e-3, atol=1e-4)
