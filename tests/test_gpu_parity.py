@@ -459,3 +459,41 @@ def test_degenerate_and_duplicate_triangles(gpu_api, ol, abi, doubles):
     ref_sum, (ref_rays, _) = ol.render_sum(holder, cam, W, H, 4, rng="philox", dielectric="stochastic", max_depth=5)
     assert ctr.rays == ref_rays
     np.testing.assert_allclose(acc, ref_sum, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_overlapping_nested_and_extreme_spheres(gpu_api, ol, abi, seed):
+    """the generators only make disjoint spheres; here they overlap, nest, span radii 1e-3 .. 3e2 and many rays
+    START INSIDE spheres (quirk Q10: tca < 0 misses even then, the far root counts when t0 < 0) or ON a sphere's
+    surface (EPSILON self-hit guard, raytracer.c:109): nearest hit == the oracle's brute-force loop in every walk"""
+    rng = np.random.default_rng(seed)
+    n = 400
+    objs = np.zeros(n, dtype=abi.OBJECT_DTYPE)
+    objs["flags"] = rng.choice([2, 4, 8, 18], n)
+    objs["radius"] = 10.0 ** rng.uniform(-3, 2.5, n)
+    objs["center"] = rng.normal(size=(n, 3)) * 20.0
+    objs["center"][0:399:7] = objs["center"][1:399:7]                           # concentric pairs (nested shells)
+    objs["color"] = rng.uniform(0, 1, (n, 3))
+    objs["emission"] = rng.uniform(0, 1, (n, 3)) * (rng.uniform(size=(n, 1)) < 0.3)
+    k = rng.integers(0, n, 6000)
+    inside = objs["center"][k[:2000]] + rng.normal(size=(2000, 3)) * 0.3 * objs["radius"][k[:2000], None]
+    u = rng.normal(size=(2000, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    on_surface = objs["center"][k[2000:4000]] + u * objs["radius"][k[2000:4000], None]
+    outside = rng.normal(size=(2000, 3)) * 60.0
+    o = np.concatenate([inside, on_surface, outside])
+    d = rng.normal(size=(6000, 3))
+    d[4000:] = objs["center"][k[4000:]] - outside + rng.normal(size=(2000, 3)) * objs["radius"][k[4000:], None]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1)
+    want = ol.intersect_rays(objs, rays)
+    with gpu_api.Scene(objs, all_trees=True) as sc:
+        for mode in (0, 1, 3, 4, 5):
+            _assert_hits_equal(sc.trace_rays(rays, use_bvh=mode), want, f"nested spheres, walk {mode}")
+        W, H = 64, 36
+        cam = gpu_api.init_camera(W, H)
+        _, acc, ctr = sc.render(cam, gpu_api.make_desc(W, H, 0, 3, max_depth=6), want_accum=True)
+    ref_sum, (ref_rays, _) = ol.render_sum(objs, cam, W, H, 3, rng="philox", dielectric="stochastic", max_depth=6)
+    assert ctr.rays == ref_rays
+    np.testing.assert_allclose(acc, ref_sum, rtol=1e-3, atol=1e-4)
+    assert (want["ids"] >= 0).mean() > 0.5
