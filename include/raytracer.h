@@ -221,6 +221,11 @@ void render_ex(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *
 
 void free_mesh(TriangleMesh *mesh);
 
+/* load_obj() with explicit parallelism (extension): the file is cut into line-aligned chunks of about
+ * `min_chunk_bytes` (0 = 4 MB) that `threads` threads (0 = the OpenMP default, at most 32) parse; the result
+ * does not depend on either argument.  load_obj(f, m) == load_obj_ex(f, m, 0, 0). */
+bool load_obj_ex(const char *filename, TriangleMesh *mesh, int threads, size_t min_chunk_bytes);
+
 /* mesh placement helper of the reference's driver (main.c:140-147) */
 void apply_matrix(TriangleMesh *mesh, mat4 matrix);
 

@@ -31,7 +31,7 @@ HOST_SYMBOLS = [
     "random_double", "random_range", "point_at", "calculate_surface_normal", "intersect_sphere",
     "intersect_triangle", "print_v", "print_m", "clamp", "init_camera", "render", "load_obj",
     "ray_count", "intersection_test_count",
-    "render_params_default", "render_scene", "render_ex", "free_mesh", "apply_matrix",
+    "render_params_default", "render_scene", "render_ex", "free_mesh", "apply_matrix", "load_obj_ex",
     "scene_default", "scene_room_walls", "scene_random_spheres", "scene_sphere_field",
     "scene_heightfield_mesh", "scene_write_obj", "scene_mesh_room", "scene_from_objects", "rt_write_png",
 ]
@@ -109,6 +109,8 @@ def _bind(cu, host):
     host.render_params_default.restype = None
     host.load_obj.argtypes = [C.c_char_p, C.POINTER(abi.TriangleMesh)]
     host.load_obj.restype = C.c_bool
+    host.load_obj_ex.argtypes = [C.c_char_p, C.POINTER(abi.TriangleMesh), C.c_int, C.c_size_t]
+    host.load_obj_ex.restype = C.c_bool
     host.free_mesh.argtypes = [C.POINTER(abi.TriangleMesh)]
     host.free_mesh.restype = None
     host.apply_matrix.argtypes = [C.POINTER(abi.TriangleMesh), C.POINTER(C.c_double)]
@@ -219,12 +221,15 @@ def apply_matrix(verts, matrix):
     return verts
 
 
-def load_obj(path):
+def load_obj(path, threads=None, min_chunk_bytes=0):
+    """load_obj (raytracer.h:158); with `threads` given, load_obj_ex (same result for any chunking)"""
     _, host = load()
-    libc = C.CDLL(None)
-    libc.free.argtypes = [C.c_void_p]
     mesh = abi.TriangleMesh()
-    if not host.load_obj(os.fsencode(path), C.byref(mesh)):
+    if threads is None:
+        ok = host.load_obj(os.fsencode(path), C.byref(mesh))
+    else:
+        ok = host.load_obj_ex(os.fsencode(path), C.byref(mesh), int(threads), C.c_size_t(min_chunk_bytes))
+    if not ok:
         raise RtbError(f"load_obj({path!r}) failed")
     n = mesh.num_triangles * 3
     arr = np.frombuffer(C.string_at(C.cast(mesh.vertices, C.c_void_p).value, 40 * n), dtype=abi.VERTEX_DTYPE).copy()

@@ -644,6 +644,19 @@ static void fill_args(RenderArgs &A, const rtb_scene *scene, const double *camer
   A.counters = scene->d_counters;
 }
 
+namespace
+{
+struct EventPair /* two CUDA events, destroyed on every return path */
+{
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair()
+  {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+} // namespace
+
 extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const rtb_render_desc *desc,
                                 float *d_accum, void *stream_, rtb_counters *counters)
 {
@@ -716,15 +729,7 @@ extern "C" int rtb_render_accum(rtb_scene *scene, const double *camera12, const 
 
   unsigned long long launches = 0;
   float phase_ms[3] = { 0.0f, 0.0f, 0.0f };
-  struct EventPair /* destroyed on every return path */
-  {
-    cudaEvent_t a = nullptr, b = nullptr;
-    ~EventPair()
-    {
-      if (a) cudaEventDestroy(a);
-      if (b) cudaEventDestroy(b);
-    }
-  } evp;
+  EventPair evp;
   cudaEvent_t &ev0 = evp.a, &ev1 = evp.b;
   if (counters)
   {
@@ -1032,7 +1037,8 @@ extern "C" int rtb_probe_l2_bandwidth(size_t bytes, int iters, int device, float
   RTB_CUDA(cudaMemset(d_buf.p, 1, n_vec * sizeof(uint4)));
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-  cudaEvent_t e0, e1;
+  EventPair ev;
+  cudaEvent_t &e0 = ev.a, &e1 = ev.b;
   RTB_CUDA(cudaEventCreate(&e0));
   RTB_CUDA(cudaEventCreate(&e1));
   k_probe_l2<<<sm_count * 8, 256>>>(d_buf.p, n_vec, 2, d_sink.p); /* warm: pull the buffer into L2 */
@@ -1042,8 +1048,6 @@ extern "C" int rtb_probe_l2_bandwidth(size_t bytes, int iters, int device, float
   RTB_CUDA(cudaEventSynchronize(e1));
   float ms = 0.0f;
   RTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *gb_per_s = (float)((double)n_vec * sizeof(uint4) * iters / (ms * 1e-3) / 1e9);
   return RTB_OK;
 }
@@ -1083,7 +1087,8 @@ extern "C" int rtb_probe_fp32_tflops(int iters, int device, float *tflops)
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
   const int blocks = sm_count * 8, threads = 256;
-  cudaEvent_t e0, e1;
+  EventPair ev;
+  cudaEvent_t &e0 = ev.a, &e1 = ev.b;
   RTB_CUDA(cudaEventCreate(&e0));
   RTB_CUDA(cudaEventCreate(&e1));
   k_probe_fp32<<<blocks, threads>>>(iters / 8 + 1, 1.0f, d_sink.p); /* warm */
@@ -1093,8 +1098,6 @@ extern "C" int rtb_probe_fp32_tflops(int iters, int device, float *tflops)
   RTB_CUDA(cudaEventSynchronize(e1));
   float ms = 0.0f;
   RTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * threads;
   *tflops = (float)(flops / (ms * 1e-3) / 1e12);
   return RTB_OK;

@@ -124,3 +124,68 @@ def test_slash_at_end_of_corner_does_not_eat_the_next_one(api, tmp_path):
     assert got.shape == (9, 5)
     assert np.array_equal(got[:, :3], np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 0], [1, 0, 0], [0, 0, 1],
                                                 [1, 0, 0], [0, 1, 0], [0, 0, 1]], float))
+
+
+def _rows(v):
+    return np.concatenate([v["pos"].reshape(-1, 3), v["tex"].reshape(-1, 2)], axis=1)
+
+
+@pytest.mark.parametrize("threads,chunk", [(1, 1 << 30), (1, 64), (3, 64), (8, 200), (4, 4096), (16, 1)])
+def test_chunked_parallel_parse_is_the_serial_parse(api, tmp_path, threads, chunk):
+    """load_obj_ex cuts the file into line-aligned chunks parsed by several threads; whatever the chunking --
+    a chunk per line, chunks that hold only `v` lines or only faces, relative indices that reach back across
+    chunks, CRLF line ends, no trailing newline -- the triangles are the one-chunk result, and the tinyobj
+    path's"""
+    rng = np.random.default_rng(11)
+    lines = ["# interleaved vertices, texcoords and faces"]
+    n_v = n_t = 0
+    for k in range(400):
+        for _ in range(rng.integers(1, 6)):
+            x, y, z = rng.uniform(-50, 50, 3)
+            lines.append(f"v {x:.7f} {y:.5g} {z:.3e}")
+            n_v += 1
+        for _ in range(rng.integers(0, 3)):
+            lines.append(f"vt {rng.uniform():.6f} {rng.uniform():.6f}")
+            n_t += 1
+        if n_v >= 5:
+            n = int(rng.integers(3, 6))
+            if rng.uniform() < 0.5:  # absolute indices anywhere before this line
+                c = [f"{rng.integers(1, n_v + 1)}" + (f"/{rng.integers(1, n_t + 1)}" if n_t else "") for _ in range(n)]
+            else:                    # relative ones, some far back
+                c = [f"-{rng.integers(1, n_v + 1)}" + (f"/-{rng.integers(1, n_t + 1)}" if n_t else "//") for _ in range(n)]
+            lines.append("f " + " ".join(c))
+    text = "\r\n".join(lines[:300]) + "\r\n" + "\n".join(lines[300:])  # first part CRLF, no newline at the end
+    p = str(tmp_path / "mixed.obj")
+    with open(p, "w", newline="") as f:
+        f.write(text)
+    serial = _rows(api.load_obj(p, threads=1, min_chunk_bytes=1 << 30))
+    got = _rows(api.load_obj(p, threads=threads, min_chunk_bytes=chunk))
+    assert len(serial) > 1500 and np.array_equal(got, serial)
+    assert np.array_equal(_rows(api.load_obj(p)), serial)
+    if os.path.exists(REF_CUBE):
+        assert np.array_equal(serial, tinyobj_load(p))
+
+
+def test_chunked_parse_of_a_segregated_file(api, tmp_path):
+    """the usual layout -- every `v`, then every `vt`, then every `f` (scene_write_obj) -- in 1 KB chunks"""
+    verts = api.heightfield_mesh(16, 10.0)
+    p = str(tmp_path / "hf.obj")
+    api.write_obj(p, verts)
+    got = api.load_obj(p, threads=5, min_chunk_bytes=1024)
+    assert np.array_equal(got["pos"], verts["pos"]) and np.array_equal(got["tex"], verts["tex"])
+
+
+@pytest.mark.parametrize("chunk", [1 << 30, 16])
+def test_parse_failures_do_not_depend_on_the_chunking(api, tmp_path, chunk):
+    """a face may only use vertices defined before it; a `v` line needs three numbers: the load fails as a whole"""
+    for name, text in (("forward.obj", "v 0 0 0\nv 1 0 0\nf 1 2 3\nv 0 1 0\n"),
+                       ("range.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 -4\n"),
+                       ("short.obj", "v 0 0 0\nv 1 0\nv 0 1 0\nf 1 2 3\n")):
+        p = str(tmp_path / name)
+        with open(p, "w") as f:
+            f.write(text)
+        with pytest.raises(api.RtbError):
+            api.load_obj(p, threads=4, min_chunk_bytes=chunk)
+    empty = str(tmp_path / "empty.obj")
+    open(empty, "w").close()
+    assert len(api.load_obj(empty, threads=4, min_chunk_bytes=chunk)) == 0
