@@ -122,6 +122,11 @@ int main(int argc, char **argv)
 
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
+  /* development aid ($RTB_TIMING): where a run of the driver spends its time */
+  const bool timing = getenv("RTB_TIMING") != NULL;
+  struct timespec tm = t0;
+#define CLI_MARK(what) do { if (timing) { struct timespec now_; clock_gettime(CLOCK_MONOTONIC, &now_); \
+    fprintf(stderr, "main: %s %.1f ms\n", what, 1e3 * (double)(now_.tv_sec - tm.tv_sec) + 1e-6 * (double)(now_.tv_nsec - tm.tv_nsec)); tm = now_; } } while (0)
 
   if (strcmp(cli.scene, "default") == 0)
   {
@@ -147,6 +152,7 @@ int main(int argc, char **argv)
     }
     else if (!load_obj(cli.scene + 4, &mesh))
       return EXIT_FAILURE;
+    CLI_MARK("mesh (generate / load_obj)");
     if (cli.placement)
     {
       /* scale, then rotate about y, then translate: M = T * Ry * S, row-major like vector.h */
@@ -158,11 +164,13 @@ int main(int argc, char **argv)
                  -s * v[0], 0, c * v[2], v[6],
                  0, 0, 0, 1 };
       apply_matrix(&mesh, m);
+      CLI_MARK("apply_matrix");
     }
     SceneObject *scene = NULL;
     Sphere *spheres = NULL;
     size_t n = scene_mesh_room(&scene, &spheres, &mesh, opt->width, opt->height);
     render_scene(framebuffer, scene, n, &camera, opt, &rp);
+    CLI_MARK("render_scene (first call: CUDA context + upload + BVH + render + read-back)");
     free(scene);
     free(spheres);
     free_mesh(&mesh);
@@ -187,6 +195,7 @@ int main(int argc, char **argv)
     free(framebuffer);
     return EXIT_FAILURE;
   }
+  CLI_MARK("write PNG");
   printf("done.\n");
   free(framebuffer);
   return EXIT_SUCCESS;
