@@ -516,7 +516,9 @@ def main_gpu(args):
             "node_visits_per_ray": node_visits_rank / hits_prof, "prim_tests_per_ray": prim_tests / max(1.0, hits_step),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(W * H * 3), "ms_per_call": [round(x, 2) for x in e2e_calls],
-                    "host_memory": "pageable (malloc'ed by the caller, like the reference's main.c)",
+                    "host_memory": "pageable (malloc'ed by the caller, like the reference's main.c); h2d_bytes_per_step counts the caller's "
+                                   "buffers -- the library's staging threads narrow float-representable vertices to 60 B per triangle, "
+                                   "so about half of the mesh bytes cross the link",
                     "pinned": e2e_pinned,
                     "api": "render_scene()/render_ex() of libraytracer_b200.so" if world == 1
                     else "rtb_render_multi(): sharded upload + all-gather + BVH build + render + ncclReduce + tonemap + D2H, all behind the C ABI"},

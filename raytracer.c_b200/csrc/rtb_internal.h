@@ -31,6 +31,11 @@ static_assert(sizeof(RefSphere) == 32, "Sphere");
 static_assert(sizeof(RefMesh) == 16, "TriangleMesh");
 static_assert(sizeof(RefSceneObject) == 96, "SceneObject");
 
+/* rtb_narrow.cpp: n_vertices Vertex records (five doubles) -> five floats each, on the host (AVX2 where the CPU has
+ * it); true when every position is float-representable */
+extern "C" bool rtb_narrow_vertices(const double *src, float *dst, size_t n_vertices);
+extern "C" bool rtb_narrow_vertices_scalar(const double *src, float *dst, size_t n_vertices);
+
 #define RT_M_REFLECTION (1u << 2)
 #define RT_M_REFRACTION (1u << 3)
 #define RT_M_CHECKERED (1u << 4)

@@ -145,6 +145,61 @@ __global__ void k_marshal_tris(const RefVertex *__restrict__ verts, int n_tris, 
   }
 }
 
+/* The same records from the narrowed upload (upload_narrowed: 15 floats per triangle, converted by the host's
+ * staging threads, every position float-representable): no double copy is written, the box of a triangle is the
+ * box of its floats. */
+__global__ void k_marshal_tris_f32(const float *__restrict__ verts, int n_tris, int obj, int gid_first,
+                                   PrimRec *__restrict__ out, float4 *__restrict__ box_lo,
+                                   float4 *__restrict__ box_hi, float2 *__restrict__ tex)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tris)
+    return;
+  const float *p = verts + 15 * (size_t)i;
+  float v[3][3], t[3][2];
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+  {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+      v[k][a] = p[5 * k + a];
+      lo[a] = fminf(lo[a], v[k][a]);
+      hi[a] = fmaxf(hi[a], v[k][a]);
+    }
+    t[k][0] = p[5 * k + 3];
+    t[k][1] = p[5 * k + 4];
+  }
+  PrimRec r;
+  r.a = make_float4(v[0][0], v[0][1], v[0][2], v[1][0]);
+  r.b = make_float4(v[1][1], v[1][2], v[2][0], v[2][1]);
+  r.c = make_float4(v[2][2], __int_as_float(gid_first + i), __uint_as_float((unsigned)obj), 0.0f);
+  out[i] = r;
+  box_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+  box_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+  if (tex)
+  {
+    tex[3 * (size_t)i + 0] = make_float2(t[0][0], t[0][1]);
+    tex[3 * (size_t)i + 1] = make_float2(t[1][0], t[1][1]);
+    tex[3 * (size_t)i + 2] = make_float2(t[2][0], t[2][1]);
+  }
+}
+
+/* A scene that needs double vertices after all (another mesh, or another rank's share, is not
+ * float-representable): the double copy of a narrowed piece is its floats, widened */
+__global__ void k_widen_tri64(const PrimRec *__restrict__ recs, int n_tris, double *__restrict__ tri64)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tris)
+    return;
+  const PrimRec r = recs[i];
+  double *o = tri64 + 9 * (size_t)i;
+  o[0] = (double)r.a.x; o[1] = (double)r.a.y; o[2] = (double)r.a.z;
+  o[3] = (double)r.a.w; o[4] = (double)r.b.x; o[5] = (double)r.b.y;
+  o[6] = (double)r.b.z; o[7] = (double)r.b.w; o[8] = (double)r.c.x;
+}
+
 /* ---- bounds ------------------------------------------------------------------- */
 
 __device__ __forceinline__ unsigned float_to_ordered(float f)
@@ -666,7 +721,7 @@ static cudaError_t pool_setup(int device)
 namespace
 {
 const size_t kStageChunk = 4u << 20;
-const int kStageMaxThreads = 8;
+const int kStageMaxThreads = 16;
 struct StageLane
 {
   char *pinned[2] = { nullptr, nullptr };
@@ -740,6 +795,68 @@ cudaError_t upload_pageable(int device, void *dst, const void *src, size_t bytes
   for (cudaError_t e : err)
     if (e != cudaSuccess)
       return e;
+  return cudaSuccess;
+}
+
+/* The narrowed form of upload_pageable for Vertex records (rtb_narrow.cpp): the staging threads convert the five
+ * doubles of a vertex to five floats while they copy, so the host writes and the link carries 60 B per triangle
+ * instead of 120 B.  *exact = false when some position is not float-representable: the device buffer then holds
+ * garbage and the caller uploads the piece as raw doubles (upload_pageable).  Returns cudaErrorNotSupported when
+ * the piece is not worth it or no page-locked memory is left (same fallback). */
+cudaError_t upload_narrowed(int device, float *dst, const RefVertex *src, size_t n_vertices, int threads, bool *exact)
+{
+  *exact = true;
+  cudaPointerAttributes attr;
+  const bool host_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  threads = std::max(1, std::min(threads, kStageMaxThreads));
+  /* whole triangles and whole groups of four vertices per chunk; small uploads get small chunks so that the
+   * first DMA starts early */
+  const size_t max_chunk = (kStageChunk / (5 * sizeof(float))) / 12 * 12;
+  size_t chunk = std::min(max_chunk, std::max<size_t>(12288, n_vertices / ((size_t)threads * 4) / 12 * 12));
+  if (host_pinned || n_vertices < 24576 || device < 0 || device >= 64)
+    return cudaErrorNotSupported;
+  StagePool &pool = g_stage[device];
+  std::lock_guard<std::mutex> lock(pool.mutex);
+  for (; pool.ready < threads; pool.ready++)
+    if (stage_lane_init(pool.lanes[pool.ready]) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return cudaErrorNotSupported;
+    }
+  const size_t n_chunks = (n_vertices + chunk - 1) / chunk;
+  std::vector<cudaError_t> err((size_t)threads, cudaSuccess);
+  std::atomic<bool> inexact(false);
+  std::vector<std::thread> workers;
+  for (int t = 0; t < threads; t++)
+    workers.emplace_back([&, t]() {
+      cudaError_t e = cudaSetDevice(device);
+      StageLane &l = pool.lanes[t];
+      int turn = 0;
+      for (size_t c = (size_t)t; c < n_chunks && e == cudaSuccess && !inexact.load(std::memory_order_relaxed);
+           c += (size_t)threads, turn++)
+      {
+        const int slot = turn & 1;
+        if (turn >= 2)
+          e = cudaEventSynchronize(l.done[slot]); /* the DMA that last read this buffer */
+        const size_t first = c * chunk, cnt = std::min(chunk, n_vertices - first);
+        if (!rtb_narrow_vertices(reinterpret_cast<const double *>(src + first), reinterpret_cast<float *>(l.pinned[slot]), cnt))
+          inexact.store(true, std::memory_order_relaxed);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(dst + 5 * first, l.pinned[slot], 5 * sizeof(float) * cnt, cudaMemcpyHostToDevice, l.stream);
+        if (e == cudaSuccess)
+          e = cudaEventRecord(l.done[slot], l.stream);
+      }
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(l.stream);
+      err[(size_t)t] = e;
+    });
+  for (std::thread &w : workers)
+    w.join();
+  for (cudaError_t e : err)
+    if (e != cudaSuccess)
+      return e;
+  *exact = !inexact.load();
   return cudaSuccess;
 }
 } // namespace
@@ -1055,6 +1172,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   BuildReadback &rb = *lease.p;
   int &h_inexact = rb.inexact;
   DevBuf<RefVertex> d_stage;
+  std::vector<std::pair<size_t, size_t>> narrowed; /* (first slot, triangles) of the pieces uploaded as floats */
   DevBuf<unsigned> d_bounds, d_vals, d_vals_sorted;
   DevBuf<BuildParams> d_bp;
   DevBuf<unsigned long long> d_keys, d_keys_sorted;
@@ -1107,9 +1225,16 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
        * device; staging is bounded so huge meshes do not double their footprint */
       const size_t chunk_tris = 1u << 21;
       /* host threads staging the pageable vertex array (see upload_pageable); ranks of one box share the host */
-      int upload_threads = sharded ? 2 : 6;
+      const int host_cores = std::max(1, (int)std::thread::hardware_concurrency());
+      int upload_threads = sharded ? std::max(2, std::min(8, host_cores / (int)G)) : 8;
       if (const char *e = getenv("RTB_UPLOAD_THREADS"))
         upload_threads = atoi(e);
+      /* narrowing pays when enough threads share the conversion (measured on the B200 box, C3's 120 MB: 8 threads
+       * 5.3 -> 4.4 ms, under the 4.5 ms of a page-locked source; 2 threads per rank lose 15 % to a plain copy).
+       * Development knob: RTB_UPLOAD_NARROW=0 / 1 */
+      bool narrow_upload = upload_threads >= 6;
+      if (const char *e = getenv("RTB_UPLOAD_NARROW"))
+        narrow_upload = atoi(e) != 0;
       /* this rank's share of the concatenated triangle list: everything, or chunk `rank` of G */
       const size_t my_first = sharded ? std::min(n_tris, tri_chunk * (size_t)shard->rank) : 0;
       const size_t my_end = sharded ? std::min(n_tris, my_first + tri_chunk) : n_tris;
@@ -1132,6 +1257,24 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
           const size_t cnt = std::min(chunk_tris, hi - g0);
           const size_t t0 = g0 - tri_first;    /* first triangle of the piece inside its mesh */
           const size_t offset = n_bs + g0;     /* its slot in the (unsorted) primitive arrays */
+          /* narrowed (60 B per triangle, converted by the staging threads) when every position of the piece is
+           * float-representable, else as raw doubles (120 B) */
+          bool exact = false;
+          cudaError_t ne = narrow_upload ? upload_narrowed(device, reinterpret_cast<float *>(d_stage.p), m.verts + 3 * t0,
+                                                           3 * cnt, upload_threads, &exact)
+                                         : cudaErrorNotSupported;
+          if (ne != cudaSuccess && ne != cudaErrorNotSupported)
+            RTB_CUDA(ne);
+          if (ne == cudaSuccess && exact)
+          {
+            k_marshal_tris_f32<<<(int)((cnt + T - 1) / T), T>>>(reinterpret_cast<const float *>(d_stage.p), (int)cnt, m.obj,
+                                                                (int)(m.gid_first + (long long)t0), d_unsorted.p + offset,
+                                                                d_lo.p + offset, d_hi.p + offset,
+                                                                want_tex ? d_tex_unsorted.p + 3 * offset : nullptr);
+            RTB_CUDA(cudaGetLastError());
+            narrowed.emplace_back(offset, cnt);
+            continue;
+          }
           RTB_CUDA(upload_pageable(device, d_stage.p, m.verts + 3 * t0, sizeof(RefVertex) * 3 * cnt, upload_threads));
           k_marshal_tris<<<(int)((cnt + T - 1) / T), T>>>(d_stage.p, (int)cnt, m.obj, (int)(m.gid_first + (long long)t0),
                                                           d_unsorted.p + offset, d_lo.p + offset, d_hi.p + offset,
@@ -1289,6 +1432,12 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
   {
     /* some mesh coordinate is not float-representable (a mesh transformed in double, main.c:140-147): keep the
      * caller's doubles, in BVH order, for the exact triangle test and the surface normal */
+    for (const std::pair<size_t, size_t> &piece : narrowed)
+    {
+      k_widen_tri64<<<(int)((piece.second + 255) / 256), 256>>>(d_unsorted.p + piece.first, (int)piece.second,
+                                                                 d_tri64_unsorted.p + 9 * piece.first);
+      RTB_CUDA(cudaGetLastError());
+    }
     if (shard != nullptr && shard->n_ranks > 1 && n_tris >= (size_t)shard->n_ranks * 4096)
     {
       /* sharded upload: every rank holds the doubles of its own triangles only (the flag is the max over the ranks,

@@ -128,6 +128,83 @@ def test_double_vertices_nearest_hit_is_bit_exact(gpu_api, ol):
         assert sc.info.double_triangles == 0
 
 
+def _with_second_mesh(abi, holder, verts):
+    """the scene of `holder` plus one more mesh object (material of the first mesh)"""
+    import ctypes as C
+    first = next(k for k in range(holder.n) if holder.objects[k].type == abi.GEOMETRY_MESH)
+    h = abi.SceneHolder()
+    h.n = holder.n + 1
+    h.objects = (abi.SceneObject * h.n)()
+    C.memmove(h.objects, holder.objects, C.sizeof(abi.SceneObject) * holder.n)
+    mesh = abi.TriangleMesh()
+    mesh.num_triangles = len(verts) // 3
+    mesh.vertices = C.cast(verts.ctypes.data, C.POINTER(abi.Vertex))
+    C.memmove(C.byref(h.objects[holder.n]), C.byref(holder.objects[first]), C.sizeof(abi.SceneObject))
+    h.objects[holder.n].geometry.mesh = C.pointer(mesh)
+    h._keep += [holder, verts, mesh]
+    return h
+
+
+def test_narrowed_upload_is_bit_exact(gpu_api, ol, abi, monkeypatch):
+    """a pageable mesh large enough for the narrowed upload (60 B per triangle, converted to float by the host's
+    staging threads): same nearest hits, points, normals and texture coordinates as the oracle's brute-force loop,
+    and the same as the raw 120 B upload (RTB_UPLOAD_NARROW=0)"""
+    W, H = 96, 54
+    verts = gpu_api.heightfield_mesh(72, 20 * W / H * 0.9)  # 10 368 triangles: above the narrowing threshold
+    holder = gpu_api.mesh_room(verts, W, H)
+    rays = random_rays_in_room_local(np.random.default_rng(29), 3000)
+    want = ol.intersect_rays(holder, rays)
+    with gpu_api.Scene(holder) as sc:
+        assert sc.info.double_triangles == 0
+        got = sc.trace_rays(rays)
+    monkeypatch.setenv("RTB_UPLOAD_NARROW", "0")
+    with gpu_api.Scene(holder) as sc:
+        raw = sc.trace_rays(rays)
+    monkeypatch.delenv("RTB_UPLOAD_NARROW")
+    hit = want["ids"] >= 0
+    assert hit.sum() > 1000
+    assert np.array_equal(got["ids"], want["ids"])
+    assert np.array_equal(got["points"][hit], want["points"][hit])
+    assert np.array_equal(got["normals"][hit], want["normals"][hit])
+    for k in ("ids", "points", "normals", "uvs"):
+        assert np.array_equal(got[k], raw[k]), k
+
+
+def test_narrowed_and_double_meshes_in_one_scene(gpu_api, ol, abi):
+    """one float-representable mesh (uploaded narrowed) and one mesh transformed in double (uploaded raw): the
+    scene keeps double vertices for BOTH -- the narrowed piece's doubles are its floats, widened -- and every
+    nearest hit equals the oracle's brute-force loop bit for bit"""
+    W, H = 96, 54
+    exact = gpu_api.heightfield_mesh(72, 20 * W / H * 0.9)
+    moved = _transformed_mesh(gpu_api, 72, W, H)
+    moved["pos"][:, 1] += 6.0  # above the first mesh
+    holder = _with_second_mesh(abi, gpu_api.mesh_room(exact, W, H), moved)
+    rays = random_rays_in_room_local(np.random.default_rng(31), 3000)
+    want = ol.intersect_rays(holder, rays)
+    with gpu_api.Scene(holder) as sc:
+        assert sc.info.double_triangles == 1
+        assert sc.info.n_triangles == (len(exact) + len(moved)) // 3
+        got = sc.trace_rays(rays)
+    hit = want["ids"] >= 0
+    n_first = len(exact) // 3
+    tri_hits = want["ids"][hit]
+    assert (tri_hits >= 6).sum() > 500  # hits on both meshes (ids follow the reference's loop order)
+    assert np.array_equal(got["ids"], want["ids"])
+    assert np.array_equal(got["points"][hit], want["points"][hit])
+    assert np.array_equal(got["normals"][hit], want["normals"][hit])
+    # and the other order: the double mesh first
+    holder2 = _with_second_mesh(abi, gpu_api.mesh_room(moved, W, H), exact)
+    want2 = ol.intersect_rays(holder2, rays)
+    with gpu_api.Scene(holder2) as sc:
+        assert sc.info.double_triangles == 1
+        got2 = sc.trace_rays(rays)
+    hit2 = want2["ids"] >= 0
+    assert np.array_equal(got2["ids"], want2["ids"])
+    assert np.array_equal(got2["points"][hit2], want2["points"][hit2])
+    assert np.array_equal(got2["normals"][hit2], want2["normals"][hit2])
+    del n_first
+
+
 def test_double_vertices_render_matches_oracle(gpu_api, ol):
     W, H = 64, 36
     verts = _transformed_mesh(gpu_api, 32, W, H)

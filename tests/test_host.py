@@ -314,3 +314,39 @@ def test_render_params_carry_num_gpus(pkg):
         os.environ.pop("RTB_NUM_GPUS", None)
         if old is not None:
             os.environ["RTB_NUM_GPUS"] = old
+
+
+# ---- narrowed mesh upload: the host-side conversion (csrc/rtb_narrow.cpp) --------------------------------
+
+def test_narrow_vertices_equals_numpy_and_flags_inexact_positions(api):
+    """15 doubles -> 15 floats per triangle: round-to-nearest like numpy, vector form == scalar form, and the
+    `exact` result is false exactly when a POSITION (not a texture coordinate) loses bits, overflows or is NaN"""
+    import ctypes as C
+    cu, _ = api.load()
+    fns = []
+    for name in ("rtb_narrow_vertices", "rtb_narrow_vertices_scalar"):
+        f = getattr(cu, name)
+        f.restype = C.c_bool
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        fns.append(f)
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 3, 4, 5, 12, 13, 1000, 4099):
+        src = rng.uniform(-50, 50, (n, 5)).astype(np.float32).astype(np.float64)
+        src[:, 3:] = rng.uniform(0, 1, (n, 2))  # texture coordinates: genuine doubles, rounded, never "inexact"
+        for f in fns:
+            dst = np.full((n, 5), -1.0, np.float32)
+            assert f(src.ctypes.data, dst.ctypes.data, n) is True
+            assert np.array_equal(dst, src.astype(np.float32))
+        if n == 0:
+            continue
+        for bad in (1.0 + 2.0 ** -40, 1e300, -1e300, float("nan"), 2.0 ** -160):
+            for v in sorted({0, n // 2, n - 1}):
+                for a in range(5):
+                    s2 = src.copy()
+                    s2[v, a] = bad
+                    for f in fns:
+                        dst = np.zeros((n, 5), np.float32)
+                        exact = f(s2.ctypes.data, dst.ctypes.data, n)
+                        assert exact is (a >= 3), (n, v, a, bad)
+                        with np.errstate(over="ignore"):
+                            assert np.array_equal(dst, s2.astype(np.float32), equal_nan=True)
