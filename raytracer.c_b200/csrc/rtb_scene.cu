@@ -1229,10 +1229,11 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
       int upload_threads = sharded ? std::max(2, std::min(8, host_cores / (int)G)) : 8;
       if (const char *e = getenv("RTB_UPLOAD_THREADS"))
         upload_threads = atoi(e);
-      /* narrowing pays when enough threads share the conversion (measured on the B200 box, C3's 120 MB: 8 threads
-       * 5.3 -> 4.4 ms, under the 4.5 ms of a page-locked source; 2 threads per rank lose 15 % to a plain copy).
-       * Development knob: RTB_UPLOAD_NARROW=0 / 1 */
-      bool narrow_upload = upload_threads >= 6;
+      /* narrowing pays when enough threads on the box share the conversion (measured on the B200 box, C3's 120 MB:
+       * 8 threads 5.3 -> 4.4 ms, under the 4.5 ms of a page-locked source; 2 ranks x 2 threads lose 15 % to a plain
+       * copy: one thread converts more slowly than it copies, many threads are bound by the host's memory system,
+       * where the narrowed form moves a third less).  Development knob: RTB_UPLOAD_NARROW=0 / 1 */
+      bool narrow_upload = upload_threads * (int)G >= 6;
       if (const char *e = getenv("RTB_UPLOAD_NARROW"))
         narrow_upload = atoi(e) != 0;
       /* this rank's share of the concatenated triangle list: everything, or chunk `rank` of G */
