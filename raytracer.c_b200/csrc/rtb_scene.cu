@@ -1226,7 +1226,7 @@ int build_scene(HostScene &hs, int device, unsigned flags, const rtb_scene_shard
       const size_t chunk_tris = 1u << 21;
       /* host threads staging the pageable vertex array (see upload_pageable); ranks of one box share the host */
       const int host_cores = std::max(1, (int)std::thread::hardware_concurrency());
-      int upload_threads = sharded ? std::max(2, std::min(8, host_cores / (int)G)) : 8;
+      int upload_threads = std::max(2, std::min(8, host_cores / (int)G));
       if (const char *e = getenv("RTB_UPLOAD_THREADS"))
         upload_threads = atoi(e);
       /* narrowing pays when enough threads on the box share the conversion (measured on the B200 box, C3's 120 MB:
