@@ -282,8 +282,10 @@ __device__ __forceinline__ uint4 wf_ld(const uint4 *p, bool stream)
 template <bool STATS, int V, bool T64 = false>
 __global__ void __launch_bounds__(128, WfTraceCfg<V>::blocks)
 k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__restrict__ n_ptr, unsigned *fetch_ctr,
-           unsigned long long *totals, int refill_idle, int node_exit, const unsigned *__restrict__ perm)
+           unsigned long long *totals, int refill_idle_word, int node_exit, const unsigned *__restrict__ perm)
 {
+  const int refill_idle = refill_idle_word & 0xFF;
+  const unsigned guided = (unsigned)(refill_idle_word >> 8); /* != 0: batches shrink with the rays left in the queue */
   constexpr bool RELOAD = (V & 1) != 0, STREAM = (V & 2) != 0;
   constexpr int WIDE = (V & 16) ? (2 + ((V >> 5) & 3)) : ((V & 8) ? 1 : 0);
   constexpr bool POP2 = (V & 128) != 0;
@@ -320,17 +322,31 @@ k_wf_trace(const __grid_constant__ SceneView sv, WfQueue q, const unsigned *__re
     {
       if (next >= end)
       {
-        unsigned base = 0;
+        unsigned base = 0, take = batch;
         if (lane == 0)
-          base = atomicAdd(fetch_ctr, batch);
+        {
+          if (guided != 0u && batch > 32u)
+          {
+            /* guided self-scheduling: a batch is this warp's share of what is left (a stale read of the
+             * cursor only changes the size, never the ownership, of a batch), so the last batches are short
+             * and the kernel's tail is one short batch, not one of 512 rays */
+            const unsigned cur_ = *reinterpret_cast<volatile unsigned *>(fetch_ctr);
+            const unsigned left = cur_ < n ? n - cur_ : 0u;
+            const unsigned cap_ = 512u << (guided >> 4);
+            take = (left / (n_warps * (guided & 15u))) & ~31u;
+            take = take < 32u ? 32u : (take > cap_ ? cap_ : take);
+          }
+          base = atomicAdd(fetch_ctr, take);
+        }
         base = __shfl_sync(WF_FULL, base, 0);
+        take = __shfl_sync(WF_FULL, take, 0);
         if (base >= n)
         {
           pool_empty = true;
           break;
         }
         next = base;
-        end = min(base + batch, n);
+        end = min(base + take, n);
       }
       const unsigned mine = next + (unsigned)__popc(bidle & ((1u << lane) - 1u));
       /* only the lanes counted in bidle take a ray: a lane served earlier in this refill whose ray
@@ -862,7 +878,14 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
 
   /* tuning word (desc->reserved): bits 0-7 refill threshold, 8-15 node-phase exit threshold,
    * 16-23 trace kernel variant; desc->reserved2: ray sorting mode (0 = off) */
-  const int refill_idle = ((desc->reserved & 0xFF) > 0 && (desc->reserved & 0xFF) <= 32) ? (desc->reserved & 0xFF) : 8;
+  int refill_idle = ((desc->reserved & 0xFF) > 0 && (desc->reserved & 0xFF) <= 32) ? (desc->reserved & 0xFF) : 8;
+  /* bits 8-15 of the word handed to k_wf_trace: guided self-scheduling of the ray batches -- a batch is
+   * min(512 << (g >> 4), rays left / (warps * (g & 15))), at least 32.  Measured default g = 1
+   * (profiles/r2_wf_tuning.md section 2i); development knob RTB_WF_GUIDED (0: fixed batches) */
+  {
+    const char *e = getenv("RTB_WF_GUIDED");
+    refill_idle |= (e ? (atoi(e) & 0xFF) : 1) << 8;
+  }
   int node_exit = (desc->reserved >> 8) & 0xFF;
   int variant = (desc->reserved >> 16) & 0xFFF;
   if (desc->reserved == 0)
