@@ -219,6 +219,12 @@ void render_scene(uint8_t *framebuffer, SceneObject *objects, size_t n_objects, 
 void render_ex(uint8_t *framebuffer, Object *objects, size_t n_objects, Camera *camera,
                Options *options, const RenderParams *params);
 
+/* Optional: starts creating the CUDA context(s) a later render*() with these parameters will use (NULL = defaults)
+ * on a background thread and returns at once.  A driver calls it first and then reads its scene -- the reference's
+ * main.c:413-429 builds the scene between allocating the frame and calling render() -- so that driver start-up
+ * (0.4-2 s per process) and scene loading overlap.  The next render*() joins the thread. */
+void render_warm_up(const RenderParams *params);
+
 void free_mesh(TriangleMesh *mesh);
 
 /* load_obj() with explicit parallelism (extension): the file is cut into line-aligned chunks of about

@@ -115,6 +115,11 @@ typedef struct
 const char *rtb_last_error(void);
 const char *rtb_version(void);
 int rtb_device_count(void);
+/* Creates the CUDA context of `device` and loads the library's kernels, so that the first scene does not pay for it
+ * (0.4-2 s on a box without a persistence daemon).  Thread-safe and optional: a driver calls it from a second thread
+ * while it still reads its scene from disk (render_warm_up() of raytracer.h; the reference's main.c:413-429 has the
+ * same order: allocate, build the scene, then render). */
+int rtb_warm_up(int device);
 
 /* scene: upload + marshal + BVH build (blocking).  The product path builds and walks ONE tree, the
  * compressed BVH4.  RTB_SCENE_ALL_TREES also keeps the BVH2 and the uncompressed BVH4 the parity

@@ -24,14 +24,14 @@ RTB_SYMBOLS = [
     "rtb_scene_info_get", "rtb_scene_destroy", "rtb_release_workspace", "rtb_render_accum", "rtb_tonemap", "rtb_render",
     "rtb_trace_rays", "rtb_path_records", "rtb_philox4x32_10", "rtb_probe_l2_bandwidth", "rtb_cast_rays",
     "rtb_probe_fp32_tflops", "rtb_render_mean", "rtb_comm_unique_id", "rtb_comm_create_rank", "rtb_comm_create_local", "rtb_comm_size",
-    "rtb_comm_local_ranks", "rtb_comm_destroy", "rtb_comm_shard_samples", "rtb_comm_scene_create", "rtb_comm_render", "rtb_render_multi",
+    "rtb_warm_up", "rtb_comm_local_ranks", "rtb_comm_destroy", "rtb_comm_shard_samples", "rtb_comm_scene_create", "rtb_comm_render", "rtb_render_multi",
 ]
 # the reference's exported surface (raytracer.h:135-164) plus the documented extensions
 HOST_SYMBOLS = [
     "random_double", "random_range", "point_at", "calculate_surface_normal", "intersect_sphere",
     "intersect_triangle", "print_v", "print_m", "clamp", "init_camera", "render", "load_obj",
     "ray_count", "intersection_test_count",
-    "render_params_default", "render_scene", "render_ex", "free_mesh", "apply_matrix", "load_obj_ex",
+    "render_params_default", "render_scene", "render_ex", "free_mesh", "apply_matrix", "load_obj_ex", "render_warm_up",
     "scene_default", "scene_room_walls", "scene_random_spheres", "scene_sphere_field",
     "scene_heightfield_mesh", "scene_write_obj", "scene_mesh_room", "scene_from_objects", "rt_write_png",
 ]

@@ -1705,3 +1705,11 @@ extern "C" void rtb_scene_destroy(rtb_scene *scene)
     rtb_cache_park(scene->device, scene->d_scratch, scene->scratch_bytes);
   delete scene;
 }
+
+extern "C" int rtb_warm_up(int device)
+{
+  RTB_CUDA(cudaSetDevice(device));
+  RTB_CUDA(cudaFree(nullptr)); /* creates the primary context */
+  RTB_CUDA(pool_setup(device));
+  return RTB_OK;
+}

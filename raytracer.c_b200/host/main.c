@@ -122,6 +122,8 @@ int main(int argc, char **argv)
 
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
+  /* the CUDA context comes up on a second thread while the scene is generated or read from disk */
+  render_warm_up(&rp);
   /* development aid ($RTB_TIMING): where a run of the driver spends its time */
   const bool timing = getenv("RTB_TIMING") != NULL;
   struct timespec tm = t0;

@@ -13,6 +13,7 @@
  */
 #include <time.h>
 #include <stdlib.h>
+#include <pthread.h>
 
 #include "raytracer.h"
 #include "rtb200.h"
@@ -165,8 +166,52 @@ static void die(const char *where)
  * float-representable; the scene upload keeps them in double for the exact triangle test. */
 void apply_matrix(TriangleMesh *mesh, mat4 matrix)
 {
-  for (size_t i = 0; i < mesh->num_triangles * 3; i++)
+  const long long n = (long long)mesh->num_triangles * 3;
+  /* every vertex on its own: the same doubles whatever the thread count */
+#pragma omp parallel for schedule(static) if (n > 65536)
+  for (long long i = 0; i < n; i++)
     mesh->vertices[i].pos = mat4_vector_mult(matrix, mesh->vertices[i].pos);
+}
+
+/* render_warm_up: CUDA contexts created on a background thread while the caller loads its scene */
+static pthread_t g_warm_thread;
+static int g_warm_running = 0;
+static int g_warm_first = 0, g_warm_count = 0;
+
+static void *warm_up_main(void *arg)
+{
+  (void)arg;
+  for (int d = g_warm_first; d < g_warm_first + g_warm_count; d++)
+    rtb_warm_up(d); /* an error shows up again, with its message, in the render call */
+  return NULL;
+}
+
+static void warm_up_join(void)
+{
+  if (g_warm_running)
+  {
+    pthread_join(g_warm_thread, NULL);
+    g_warm_running = 0;
+  }
+}
+
+void render_warm_up(const RenderParams *params)
+{
+  RenderParams p;
+  if (params)
+    p = *params;
+  else
+    render_params_default(&p);
+  warm_up_join();
+  g_warm_first = p.num_gpus > 1 ? 0 : p.device;
+  g_warm_count = p.num_gpus > 1 ? p.num_gpus : 1;
+  static int at_exit_set = 0;
+  if (!at_exit_set)
+  {
+    atexit(warm_up_join); /* a driver that gives up before it renders must not exit under a starting context */
+    at_exit_set = 1;
+  }
+  g_warm_running = pthread_create(&g_warm_thread, NULL, warm_up_main, NULL) == 0;
 }
 
 static void fill_desc(rtb_render_desc *desc, const Options *options, const RenderParams *p)
@@ -224,6 +269,7 @@ static void render_records(uint8_t *framebuffer, const void *objects, size_t n_o
     p.max_depth = MAX_DEPTH;
   if (p.num_gpus < 1)
     p.num_gpus = 1;
+  warm_up_join(); /* a render_warm_up() still creating contexts */
 
   rtb_render_desc desc;
   fill_desc(&desc, options, &p);

@@ -350,3 +350,26 @@ def test_narrow_vertices_equals_numpy_and_flags_inexact_positions(api):
                         assert exact is (a >= 3), (n, v, a, bad)
                         with np.errstate(over="ignore"):
                             assert np.array_equal(dst, s2.astype(np.float32), equal_nan=True)
+
+
+def test_apply_matrix_is_the_same_for_any_thread_count(api, monkeypatch):
+    """apply_matrix (main.c:140-147) runs over the host cores for large meshes: vertex by vertex the result is the
+    scalar mat4_vector_mult of the reference, bit for bit"""
+    verts = api.heightfield_mesh(120, 10.0)  # 28 800 triangles: above the parallel threshold
+    assert len(verts) > 65536
+    m = np.array([[0.7, 0.1, 0.0, 0.123456789], [0.0, 1.3, -0.2, 1.0 / 3.0], [0.3, 0.0, 0.9, -2.0 / 7.0], [0, 0, 0, 1.0]])
+    want = verts["pos"].copy()
+    # mat4_vector_mult (vector.h:63-74): row . (x, y, z, 1), left to right
+    x, y, z = want[:, 0].copy(), want[:, 1].copy(), want[:, 2].copy()
+    for r in range(3):
+        want[:, r] = ((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3] * 1.0
+    got = api.apply_matrix(verts.copy(), m)
+    assert np.array_equal(got["pos"], want)
+    assert np.array_equal(got["tex"], verts["tex"])
+
+
+def test_render_warm_up_returns_at_once_and_never_fails(api):
+    """render_warm_up() only starts a thread; without a GPU the thread's error is dropped (the render call reports it)"""
+    _, host = api.load()
+    host.render_warm_up(None)
+    host.render_warm_up(None)  # joins the first, starts another; the library joins at exit
