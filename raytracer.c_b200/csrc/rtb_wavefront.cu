@@ -992,7 +992,9 @@ int wf_render(rtb_scene *scene, RenderArgs &A, const rtb_render_desc *desc, floa
 
   RTB_CUDA(cudaMemsetAsync(planes, 0, slots * 16, stream));
 
-  const int shade_blocks = sm_count * 16;
+  int shade_blocks = sm_count * 16;
+  if (const char *e = getenv("RTB_WF_SHADE_BLOCKS")) /* development knob: blocks per SM of the grid-stride shade kernel */
+    shade_blocks = sm_count * std::max(1, atoi(e));
 
   /* per-kernel timing (only with counters): events around every trace launch */
   struct EventList : std::vector<cudaEvent_t> /* destroyed on every return path */
