@@ -373,3 +373,37 @@ def test_render_warm_up_returns_at_once_and_never_fails(api):
     _, host = api.load()
     host.render_warm_up(None)
     host.render_warm_up(None)  # joins the first, starts another; the library joins at exit
+
+
+# ---- bench.py: the two arms of the measurement contract ----------------------------------------------------
+
+def _run_bench(*args, timeout=300):
+    import json as _json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    return out, (_json.loads(lines[-1]) if lines else None)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` times the reference's CPU implementation (C1: the unmodified program of
+    oracle/_ref, else the oracle port) and prints ONE JSON line with the keys the driver reads"""
+    out, line = _run_bench("--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0")
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert line is not None, out.stdout[-2000:]
+    assert line["impl"] == "reference" and line["metric"] == "Mrays/s" and line["unit"] == "Mrays/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert "c1" in line["config"]["workload"]
+
+
+def test_bench_gpu_arm_fails_loudly_without_a_gpu(api):
+    """no CUDA device -> the product arm refuses to run (there is no CPU fallback to time by mistake)"""
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    out, line = _run_bench("--steps", "1", "--warmup", "1", timeout=120)
+    assert out.returncode != 0 and line is None
+    assert "CUDA device" in (out.stderr + out.stdout)
