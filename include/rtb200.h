@@ -5,7 +5,8 @@
  * What each entry point replaces in the reference (/root/reference):
  *   rtb_scene_create*      the implicit "scene" = the Object[] the caller hands to
  *                          render() (raytracer.h:156, main.c:256-397, main.c:429); here it
- *                          is uploaded once, converted AoS-double -> SoA on the device and
+ *                          is uploaded once (a pageable Vertex array is narrowed to floats on the way up when
+ *                          every position is float-representable), converted AoS-double -> SoA on the device and
  *                          a BVH is built over it (replaces the O(n) loop of intersect(),
  *                          raytracer.c:393-464)
  *   rtb_render_accum       the loop nest of render() up to the per-pixel sum
@@ -18,6 +19,8 @@
  *   rtb_cast_rays          cast_ray() for arbitrary rays (raytracer.c:556-641): parity probe of the
  *                          Whitted integrator (rtb_render_desc.integrator = RTB_INTEGRATOR_WHITTED)
  *   rtb_philox4x32_10      random_double()'s replacement (raytracer.c:227): KAT probe
+ *   rtb_warm_up            no reference counterpart: creates the CUDA context early (a driver calls it on a second
+ *                          thread while it reads its scene, main.c:413-429)
  *   rtb_probe_l2_bandwidth, rtb_probe_fp32_tflops   no reference counterpart: measure the L2 and FP32 roofline denominators
  *   rtb_comm_*, rtb_render_multi   render() on all GPUs of the box: spp-sharded, ONE ncclReduce of the
  *                          float sums, sharded scene upload + all-gather (no reference counterpart:
