@@ -12,7 +12,11 @@
 #include <stdlib.h>
 #include <string.h>
 
-static uint32_t crc_table[256];
+/* CRC-32 (PNG, polynomial 0xEDB88320), eight bytes per step ("slicing by 8"): table k holds the CRC of a byte
+ * followed by k zero bytes.  The frame of a 1080p render is 6 MB; with a byte-at-a-time CRC and an Adler-32 that
+ * took a modulo per byte, writing it cost 65 ms on the build container (38 ms on the B200 box's host), with this
+ * form 27 ms, most of it the two copies and the fwrite. */
+static uint32_t crc_table[8][256];
 static int crc_ready = 0;
 
 static void crc_init(void)
@@ -22,16 +26,48 @@ static void crc_init(void)
     uint32_t c = n;
     for (int k = 0; k < 8; k++)
       c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
-    crc_table[n] = c;
+    crc_table[0][n] = c;
   }
+  for (uint32_t n = 0; n < 256; n++)
+    for (int k = 1; k < 8; k++)
+      crc_table[k][n] = crc_table[0][crc_table[k - 1][n] & 0xFF] ^ (crc_table[k - 1][n] >> 8);
   crc_ready = 1;
 }
 
 static uint32_t crc_update(uint32_t crc, const uint8_t *buf, size_t len)
 {
-  for (size_t i = 0; i < len; i++)
-    crc = crc_table[(crc ^ buf[i]) & 0xFF] ^ (crc >> 8);
+  size_t i = 0;
+  for (; i + 8 <= len; i += 8)
+  {
+    /* bytes are combined explicitly: no alignment or endianness assumption */
+    const uint32_t lo = crc ^ ((uint32_t)buf[i] | (uint32_t)buf[i + 1] << 8 | (uint32_t)buf[i + 2] << 16 | (uint32_t)buf[i + 3] << 24);
+    crc = crc_table[7][lo & 0xFF] ^ crc_table[6][(lo >> 8) & 0xFF] ^ crc_table[5][(lo >> 16) & 0xFF] ^ crc_table[4][lo >> 24] ^
+          crc_table[3][buf[i + 4]] ^ crc_table[2][buf[i + 5]] ^ crc_table[1][buf[i + 6]] ^ crc_table[0][buf[i + 7]];
+  }
+  for (; i < len; i++)
+    crc = crc_table[0][(crc ^ buf[i]) & 0xFF] ^ (crc >> 8);
   return crc;
+}
+
+/* Adler-32 with the modulo deferred: 5552 is the largest n with 255 n (n + 1) / 2 + (n + 1)(65521 - 1) < 2^32 (zlib's NMAX) */
+static void adler_update(uint32_t *pa, uint32_t *pb, const uint8_t *buf, size_t len)
+{
+  uint32_t a = *pa, b = *pb;
+  while (len > 0)
+  {
+    const size_t n = len < 5552 ? len : 5552;
+    for (size_t i = 0; i < n; i++)
+    {
+      a += buf[i];
+      b += a;
+    }
+    a %= 65521u;
+    b %= 65521u;
+    buf += n;
+    len -= n;
+  }
+  *pa = a;
+  *pb = b;
 }
 
 static void put_u32(uint8_t *p, uint32_t v)
@@ -103,11 +139,7 @@ int rt_write_png(const char *filename, int w, int h, int comp, const void *data,
     z[o++] = (uint8_t)(~len & 0xFF);
     z[o++] = (uint8_t)((~len >> 8) & 0xFF);
     memcpy(z + o, raw + pos, len);
-    for (size_t i = 0; i < len; i++)
-    {
-      a = (a + raw[pos + i]) % 65521u;
-      b = (b + a) % 65521u;
-    }
+    adler_update(&a, &b, raw + pos, len);
     o += len;
     pos += len;
   }

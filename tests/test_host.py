@@ -214,7 +214,10 @@ def test_png_writer(api, tmp_path):
     rng = np.random.default_rng(0)
     img = rng.integers(0, 256, size=(37, 211, 3), dtype=np.uint8)  # > 65535 bytes: several stored blocks
     big = rng.integers(0, 256, size=(200, 300, 3), dtype=np.uint8)
-    for k, im in enumerate((img, big)):
+    white = np.full((1080, 1920, 3), 255, np.uint8)  # worst case for the deferred Adler-32 modulo; the bench frame size
+    tiny = rng.integers(0, 256, size=(1, 1, 3), dtype=np.uint8)  # shorter than one 8-byte CRC step
+    odd = rng.integers(0, 256, size=(5, 3, 3), dtype=np.uint8)
+    for k, im in enumerate((img, big, white, tiny, odd)):
         p = tmp_path / f"o{k}.png"
         assert host.rt_write_png(str(p).encode(), im.shape[1], im.shape[0], 3, im.ctypes.data, im.shape[1] * 3) != 0
         assert np.array_equal(_read_png(str(p)), im)
