@@ -120,6 +120,26 @@ def test_wavefront_equals_megakernel_on_a_mesh(gpu_api, spp, planes):
     assert c2.node_visits == c0.node_visits and c2.prim_tests == c0.prim_tests  # same BVH2, same order
 
 
+def test_guided_ray_batches_change_nothing_but_the_schedule(gpu_api, monkeypatch):
+    """k_wf_trace sizes its ray batches by the rays left in the queue (guided self-scheduling; only launches with
+    more than 32 rays per warp and batch, hence a 720p frame): sums, ray counts and primitive-test counts equal
+    those of fixed batches, bit for bit"""
+    W, H = 1280, 720
+    holder = gpu_api.mesh_room(gpu_api.heightfield_mesh(96, 20 * W / H * 0.98), W, H)
+    cam = gpu_api.init_camera(W, H)
+    desc = gpu_api.make_desc(W, H, 0, 2, max_depth=5, profile=1)
+    out = {}
+    with gpu_api.Scene(holder) as sc:
+        for g in ("0", "1", "34"):  # fixed; the default rule; rays left / (2 warps) with a 2 048 cap
+            monkeypatch.setenv("RTB_WF_GUIDED", g)
+            _, acc, ctr = sc.render(cam, desc, want_accum=True)
+            out[g] = (acc.copy(), ctr.rays, ctr.prim_tests, ctr.node_visits, ctr.rays_intersected)
+    monkeypatch.delenv("RTB_WF_GUIDED")
+    for g in ("1", "34"):
+        assert np.array_equal(out[g][0], out["0"][0]), g
+        assert out[g][1:] == out["0"][1:], g
+
+
 def test_counters_without_profiling(gpu_api):
     """rtb_render_desc.profile = 0 (what the drop-in render() uses): same sums, same ray and
     primitive-test counts, no node-visit count, no per-kernel times"""
